@@ -1,0 +1,151 @@
+/*
+ * vcla.h -- C ABI of the B200-native VisualCLA multimodal forward path (libvcla.so).
+ *
+ * This is the drop-in boundary for ONE hot path of airaria/Visual-Chinese-LLaMA-Alpaca:
+ *   image + prompt -> CLIP-ViT-L/14 -> post_layernorm -> 6-layer Resampler -> projector
+ *   -> splice into the text embeddings -> LLaMA-7B prefill + KV-cache greedy decode.
+ * The reference is pure Python and has no FFI of its own; each entry point
+ * below names the reference code it replaces (paths relative to the reference repo root, `HF:` =
+ * transformers 5.5.0).  The Python package `visualcla` (visual-chinese-llama-alpaca_b200/visualcla)
+ * binds these with ctypes and exposes the reference's own API (VisualCLAModel.generate/.forward,
+ * chat, get_model_and_tokenizer_and_processor).  See INTEGRATION.md for the binding stub.
+ *
+ * Conventions: plain pointers and sizes, no torch / C++ types; every function returns 0 on success,
+ * non-zero on failure with a message retrievable through vcla_last_error() (thread-local); nothing
+ * throws across the ABI.  "dev" pointers are CUDA device pointers on the context's device; the
+ * library never frees caller memory.  One context per GPU, calls externally serialised.  Every call
+ * that takes a `stream` only enqueues work on it (no host synchronisation) unless documented.
+ */
+#ifndef VCLA_H_
+#define VCLA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vcla_ctx vcla_ctx;
+typedef void* vcla_stream; /* cudaStream_t */
+
+/* element types of caller buffers */
+enum { VCLA_F32 = 0, VCLA_F16 = 1, VCLA_BF16 = 2 };
+
+/* image layouts of the prompt (models/visualcla/modeling_visualcla.py:290-305 / :356-370) */
+enum {
+  VCLA_TEXT_ONLY = 0,       /* pixel_values=None: multimodal_embeds = input_embeds (:378-380) */
+  VCLA_IMAGE_AT_HEAD = 1,   /* [e0,e1, img x nq, e2...]  (:291/:357); S = T + nq */
+  VCLA_IMAGE_PLACEHOLDER = 2 /* image rows replace the nq <img_token> slots after <img> (:293-305); S = T */
+};
+
+/* Shapes of the path.  Mirrors VisualCLAConfig / VisualResamplerConfig / the HF CLIP + LLaMA configs
+ * (models/visualcla/configuration_visualcla.py:10-39, modeling_visual_resampler.py:90-129). */
+typedef struct {
+  /* CLIP-ViT (HF:models/clip/modeling_clip.py) */
+  int v_hidden, v_layers, v_heads, v_ffn, v_patch, v_image;
+  float v_eps;
+  /* Resampler (models/visualcla/modeling_visual_resampler.py) */
+  int r_hidden, r_layers, r_heads, r_ffn, r_queries;
+  float r_eps;
+  /* LLaMA (HF:models/llama/modeling_llama.py) */
+  int t_hidden, t_layers, t_heads, t_ffn, t_vocab;
+  float t_eps, rope_theta;
+  /* capacity of this context */
+  int max_batch;           /* sequences resident at once (per GPU) */
+  int max_seq;             /* prompt + generated tokens per sequence */
+  int max_prefill_tokens;  /* max B*S of one prefill call */
+  int page_tokens;         /* tokens per KV-cache page (default 64 if 0) */
+} vcla_config;
+
+const char* vcla_last_error(void);
+const char* vcla_version(void);
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Allocates the weight arena, paged KV cache and activation buffers on the current CUDA device.
+ * Replaces model construction: VisualCLAModel.__init__ (modeling_visualcla.py:70-108). */
+int vcla_create(const vcla_config* cfg, vcla_ctx** out);
+void vcla_destroy(vcla_ctx* ctx);
+int vcla_get_config(const vcla_ctx* ctx, vcla_config* out);
+/* bytes of device memory held by the context (weights, kv, activations) */
+int vcla_memory_bytes(const vcla_ctx* ctx, int64_t* weights, int64_t* kv, int64_t* activations);
+
+/* ---- weights ---------------------------------------------------------------------------------- */
+/* The logical tensors are addressed by the reference's own state-dict names
+ * (VisualCLAModel.state_dict(): "vision_model.vision_model.*", "visual_resampler.*",
+ * "image_projection_layer.*", "text_model.model.*", "text_model.lm_head.weight"; merged checkpoint
+ * layout scripts/merge_llama_with_visualcla_lora.py:92-97, read back at modeling_visualcla.py:141-179). */
+int vcla_weight_count(const vcla_ctx* ctx);
+/* kind: 0 = matrix stored bf16, 1 = vector/table stored f32.  shape has up to 4 dims. */
+int vcla_weight_info(const vcla_ctx* ctx, int index, const char** name, int64_t shape[4], int* ndim, int* kind);
+/* Copy + repack one tensor into the arena (fused QKV, gate/up interleave, K padding).  `src` is a host
+ * pointer (on_device = 0) or device pointer (on_device = 1) to the contiguous tensor in `dtype`.
+ * Replaces from_merged_pretrained's loading (modeling_visualcla.py:120-181).  Synchronises the stream. */
+int vcla_load_weight(vcla_ctx* ctx, const char* name, const void* src, int dtype, int on_device, vcla_stream stream);
+/* Copy one logical tensor back to host: bf16 for kind 0, f32 for kind 1 (state_dict() equivalent). */
+int vcla_read_weight(vcla_ctx* ctx, const char* name, void* dst_host, vcla_stream stream);
+/* Deterministic synthetic weights: w = mean + std * IrwinHall4(hash(name, seed, index)), bit-identical
+ * to oracle/visualcla_oracle.py:hash_normal_bf16 (std/mean per tensor as in oracle weight_specs). */
+int vcla_init_synthetic(vcla_ctx* ctx, uint32_t seed, vcla_stream stream);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+/* Drop all sequences (KV cache lengths -> 0). */
+int vcla_reset(vcla_ctx* ctx, vcla_stream stream);
+
+/* pixels (B,3,I,I) NCHW -> image embeddings (B, r_queries, t_hidden), kept inside the context for the
+ * next vcla_prefill and optionally copied to `out_dev_f32`.  Replaces
+ *   vision_model(pixel_values) -> post_layernorm -> visual_resampler -> image_projection_layer
+ * (modeling_visualcla.py:283-288 / :349-354; HF:models/clip/modeling_clip.py:667-692;
+ *  modeling_visual_resampler.py:609-737). */
+int vcla_vision_encode(vcla_ctx* ctx, const void* pixels_dev, int pixel_dtype, int B, float* out_dev_f32, vcla_stream stream);
+
+/* Prefill B prompts of T tokens each (equal length, unpadded; position_ids = arange).
+ *   ids_dev        int64 (B,T) device
+ *   image_mode     VCLA_TEXT_ONLY / VCLA_IMAGE_AT_HEAD / VCLA_IMAGE_PLACEHOLDER
+ *   img_row_dev    int32 (B) device: first row of the image block inside each sequence (index of <img> + 1),
+ *                  -1 = no image for this sample; ignored for TEXT_ONLY; for AT_HEAD pass NULL (row 2)
+ *   logits_all_dev f32 (B,S,V) or NULL   -- VisualCLAModel.forward(...).logits (modeling_visualcla.py:321-328)
+ *   last_logits_dev f32 (B,V) or NULL    -- logits of the last position (what generate() samples from)
+ *   next_tok_dev   int32 (B) or NULL     -- argmax of last_logits (greedy)
+ * Fills the KV cache; sequence length becomes S.  Replaces the splice (modeling_visualcla.py:290-312 /
+ * :356-377) + LlamaForCausalLM prefill (HF:models/llama/modeling_llama.py:375-501). */
+int vcla_prefill(vcla_ctx* ctx, const int64_t* ids_dev, int B, int T, int image_mode, const int32_t* img_row_dev,
+                 float* logits_all_dev, float* last_logits_dev, int32_t* next_tok_dev, vcla_stream stream);
+
+/* One greedy decode step for the B resident sequences: consumes tok_in_dev (int32 (B)), appends its K/V,
+ * writes logits (f32 (B,V), optional) and the argmax (int32 (B)).  Captured into a CUDA graph on first use
+ * (per distinct argument tuple) when use_graph != 0.  Replaces one iteration of
+ * GenerationMixin._sample (HF:generation/utils.py:2743-2810) incl. DynamicCache.update (HF:cache_utils.py:119-120). */
+int vcla_decode_step(vcla_ctx* ctx, const int32_t* tok_in_dev, int B, float* logits_dev, int32_t* tok_out_dev, int use_graph,
+                     vcla_stream stream);
+
+/* number of this library's kernels launched by the context since the last call with reset != 0 */
+int64_t vcla_kernel_launches(vcla_ctx* ctx, int reset);
+
+/* ---- introspection for parity tests ---------------------------------------------------------- */
+/* Copy an internal fp32 activation to the host (synchronises): "vit_out" (B,tokens,v_hidden), "post_ln",
+ * "resampler_out" (B,nq,r_hidden), "projector_out" (B,nq,t_hidden), "inputs_embeds" n/a after prefill. */
+int vcla_read_stage(vcla_ctx* ctx, const char* stage, int B, float* dst_host, vcla_stream stream);
+
+/* ---- operator-level entry points (kernel parity tests, micro-benchmarks) ---------------------- */
+/* D = A[M,K] * W[N,K]^T on the tcgen05 path.  mode: 0 store bf16 (act: 0 none, 1 quick_gelu, 2 gelu),
+ * 1 fp32 (accumulate flag), 2 SwiGLU (W rows interleaved [32 gate|32 up]), 3 swap-AB split-K partials
+ * (out f32 [splits][M_b][N] with A = weights).  use_reference != 0 runs the naive CUDA-core kernel instead. */
+int vcla_op_gemm(const void* A_dev_bf16, const void* W_dev_bf16, int M, int N, int K, int mode, int act, int accumulate,
+                 const float* bias_dev, void* out_dev, int ldo, int splits, int tile_n, int use_reference, vcla_stream stream);
+int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1,
+                      const void* v1, int kv1_stride, int n1, void* out, int o_stride, int B, int H, int Sq, int HD, float scale,
+                      int causal, vcla_stream stream);
+int vcla_op_layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps, void* y_bf16, float* y_f32,
+                      vcla_stream stream);
+int vcla_op_rmsnorm(const float* x, int rows, int D, const float* w, float eps, void* y_bf16, vcla_stream stream);
+/* Micro-benchmark of ONE decode weight-streaming GEMM shape (which: 0 fused QKV, 1 o_proj, 2 fused gate/up, 3 down_proj,
+ * 4 lm_head) over every layer's distinct weights with batch B, timed with CUDA events on `stream`; returns the mean
+ * microseconds per kernel launch and the algorithmic weight bytes one launch streams.  Synchronises. */
+int vcla_bench_decode_gemm(vcla_ctx* ctx, int which, int B, int reps, float* avg_us, int64_t* weight_bytes, vcla_stream stream);
+/* enable/disable programmatic dependent launch for subsequently enqueued kernels (process-wide) */
+void vcla_set_pdl(int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCLA_H_ */

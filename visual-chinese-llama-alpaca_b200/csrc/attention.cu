@@ -1,0 +1,398 @@
+// Attention kernels of the VisualCLA path.
+//
+//  attention_prefill : flash-style fused softmax(QK^T)V for ViT (non-causal, S=257, hd 64), the Resampler
+//                      (64 queries over [64 query-rows ; 257 image rows] = two KV segments, hd 64) and LLaMA prefill
+//                      (causal, hd 128).  Attention is <3 % of the path's FLOPs, so this uses the
+//                      register-fragment tensor path (mma.sync m16n8k16) with fp32 online softmax; the dense
+//                      contractions that dominate run on tcgen05 (gemm.cu).
+//  attention_decode  : one new token per sequence against the paged KV cache.  HBM-bound.  Fuses: split-K
+//                      reduction of the QKV projection partials, RoPE, KV-cache append, split-KV attention and the
+//                      final cross-split combine (last-arriving CTA, fixed order => deterministic).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vcla {
+
+// =================================================================================================
+// prefill
+// =================================================================================================
+template <int HD>
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {  // byte offset of 16 B chunk in a [rows][HD] bf16 tile
+  return (uint32_t)(row * (HD * 2) + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
+  constexpr int BQ = 64, BKV = 64, CHUNKS = HD / 8;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem), sK = sQ + BQ * HD * 2, sV = sK + BKV * HD * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int Sk = c.n0 + c.n1;
+  const int off = Sk - c.Sq;  // causal: kv j visible to query i iff j <= i + off
+
+  pdl_wait();
+  pdl_launch_dependents();
+
+  // ---- Q tile -> smem
+  for (int i = tid; i < BQ * CHUNKS; i += 128) {
+    int r = i / CHUNKS, ch = i % CHUNKS;
+    int qi = q0 + r;
+    bool ok = qi < c.Sq;
+    const bf16* src = c.q + ((size_t)(b * c.Sq + (ok ? qi : 0)) * c.q_stride + h * HD + ch * 8);
+    cp_async_16(sQ + swz<HD>(r, ch), src, ok);
+  }
+  cp_async_commit();
+
+  float o_acc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const float sl2 = c.scale * 1.4426950408889634f;
+
+  int kv_end = Sk;
+  if (c.causal) kv_end = min(Sk, q0 + BQ + off);
+  const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;  // the two query rows this thread owns
+
+  for (int j0 = 0; j0 < kv_end; j0 += BKV) {
+    __syncthreads();  // previous tile fully consumed
+    for (int i = tid; i < BKV * CHUNKS; i += 128) {
+      int r = i / CHUNKS, ch = i % CHUNKS;
+      int j = j0 + r;
+      bool ok = j < Sk;
+      const bf16 *ks, *vs;
+      if (j < c.n0 || !ok) {
+        int jj = ok ? j : 0;
+        size_t ro = (size_t)(b * c.n0 + jj) * c.kv0_stride + h * HD + ch * 8;
+        ks = c.k0 + ro; vs = c.v0 + ro;
+      } else {
+        size_t ro = (size_t)(b * c.n1 + (j - c.n0)) * c.kv1_stride + h * HD + ch * 8;
+        ks = c.k1 + ro; vs = c.v1 + ro;
+      }
+      cp_async_16(sK + swz<HD>(r, ch), ks, ok);
+      cp_async_16(sV + swz<HD>(r, ch), vs, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---- S = Q K^T  (16 x 64 per warp)
+    float s[BKV / 8][4];
+#pragma unroll
+    for (int i = 0; i < BKV / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4(a, sQ + swz<HD>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+#pragma unroll
+      for (int nt = 0; nt < BKV / 8; nt += 2) {
+        uint32_t kb[4];
+        const int m = lane >> 3;
+        ldmatrix_x4(kb, sK + swz<HD>((nt + (m >> 1)) * 8 + (lane & 7), ks * 2 + (m & 1)));
+        uint32_t b0[2] = {kb[0], kb[1]}, b1[2] = {kb[2], kb[3]};
+        mma_bf16_16816(s[nt], a, b0);
+        mma_bf16_16816(s[nt + 1], a, b1);
+      }
+    }
+    // ---- mask + online softmax (fp32)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < BKV / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int j = j0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+        int qi = (e < 2) ? r0 : r1;
+        bool vis = (j < Sk) && (!c.causal || j <= qi + off);
+        float v = vis ? s[nt][e] * sl2 : -INFINITY;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float corr[2], msafe[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      float mnew = fmaxf(m_run[r], mx[r]);
+      msafe[r] = (mnew == -INFINITY) ? 0.f : mnew;
+      corr[r] = exp2f(m_run[r] - msafe[r]);
+      m_run[r] = mnew;
+      l_run[r] *= corr[r];
+    }
+    float ls[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < BKV / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float pv = exp2f(s[nt][e] - msafe[e >> 1]);
+        s[nt][e] = pv;
+        ls[e >> 1] += pv;
+      }
+    }
+    l_run[0] += ls[0];
+    l_run[1] += ls[1];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+      o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+    }
+    // ---- O += P V
+#pragma unroll
+    for (int kk = 0; kk < BKV / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < HD / 8; nd += 2) {
+        uint32_t vb[4];
+        const int m = lane >> 3;
+        ldmatrix_x4_trans(vb, sV + swz<HD>(kk * 16 + (m & 1) * 8 + (lane & 7), nd + (m >> 1)));
+        uint32_t b0[2] = {vb[0], vb[1]}, b1[2] = {vb[2], vb[3]};
+        mma_bf16_16816(o_acc[nd], a, b0);
+        mma_bf16_16816(o_acc[nd + 1], a, b1);
+      }
+    }
+  }
+  // ---- finalise: O / l  (l summed over the 4 lanes that share a row)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
+  const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
+#pragma unroll
+  for (int nd = 0; nd < HD / 8; ++nd) {
+    const int d = nd * 8 + (lane & 3) * 2;
+    if (r0 < c.Sq) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(c.out + (size_t)(b * c.Sq + r0) * c.o_stride + h * HD + d);
+      *dst = pack_bf16x2(o_acc[nd][0] * inv0, o_acc[nd][1] * inv0);
+    }
+    if (r1 < c.Sq) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(c.out + (size_t)(b * c.Sq + r1) * c.o_stride + h * HD + d);
+      *dst = pack_bf16x2(o_acc[nd][2] * inv1, o_acc[nd][3] * inv1);
+    }
+  }
+}
+
+int attention_prefill(const AttnCall& c, cudaStream_t st) {
+  if (c.HD != 64 && c.HD != 128) { set_error("attention_prefill: head dim %d unsupported (64/128)", c.HD); return -1; }
+  if ((c.q_stride % 8) || (c.kv0_stride % 8) || (c.n1 > 0 && (c.kv1_stride % 8)) || (c.o_stride % 2)) {
+    set_error("attention_prefill: strides must keep 16 B alignment");
+    return -1;
+  }
+  dim3 grid((c.Sq + 63) / 64, c.H, c.B);
+  const size_t smem = 3 * 64 * c.HD * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  if (c.HD == 64) {
+    VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_prefill_kernel<64>, c));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VCLA_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_prefill_kernel<128>, c));
+  }
+  return 0;
+}
+
+// =================================================================================================
+// decode (hd = 128): grid (kv_splits, H, B), 128 threads
+// =================================================================================================
+__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+                                                          const float* __restrict__ rope_sin) {
+  constexpr int HD = 128;
+  __shared__ float s_q[HD];
+  __shared__ float s_k[HD];
+  __shared__ float s_v[HD];
+  __shared__ float s_acc[4][HD];
+  __shared__ float s_m[4], s_l[4];
+  __shared__ int s_last;
+
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = c.H * HD;
+
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int L = c.seq_len[b];          // tokens already cached; the new token gets index L
+  const int n = L + 1;
+  int chunk = (n + c.kv_splits - 1) / c.kv_splits;
+  chunk = (chunk + 15) & ~15;
+  const int t_begin = split * chunk;
+  const int t_end = min(n, t_begin + chunk);
+  const bool owns_new = (t_begin <= L) && (L < t_end);
+
+  // ---- reduce the split-K partials of this head's q (and k, v if this CTA owns the new token); RoPE
+  {
+    const int d = tid;
+    float qv = 0.f, kv = 0.f, vv = 0.f;
+    for (int s = 0; s < c.splits; ++s) {
+      const float* row = c.qkv_partial + ((size_t)s * c.ws_rows + b) * (size_t)(3 * T);
+      qv += row[h * HD + d];
+      if (owns_new) { kv += row[T + h * HD + d]; vv += row[2 * T + h * HD + d]; }
+    }
+    s_q[d] = qv; s_k[d] = kv; s_v[d] = vv;
+    __syncthreads();
+    const float cs = rope_cos[(size_t)L * (HD / 2) + (d & 63)], sn = rope_sin[(size_t)L * (HD / 2) + (d & 63)];
+    const float qp = (d < 64) ? -s_q[d + 64] : s_q[d - 64];
+    const float kp = (d < 64) ? -s_k[d + 64] : s_k[d - 64];
+    const float qr = (qv * cs + qp * sn) * c.scale;
+    const float kr = kv * cs + kp * sn;
+    __syncthreads();
+    s_q[d] = qr;
+    if (owns_new) {
+      // the cache holds bf16; attend over the same rounded values every later step will read
+      const bf16 kb = __float2bfloat16(kr), vb = __float2bfloat16(vv);
+      s_k[d] = __bfloat162float(kb);
+      s_v[d] = __bfloat162float(vb);
+      const int page = c.page_table[(size_t)b * c.pages_per_seq + L / c.page_tokens];
+      const int slot = L % c.page_tokens;
+      bf16* kdst = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD;
+      bf16* vdst = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * c.page_tokens + slot) * HD;
+      kdst[d] = kb;
+      vdst[d] = vb;
+    }
+    __syncthreads();
+  }
+
+  // ---- attention over cached tokens [t_begin, min(t_end, L)): 8 lanes per token, 16 dims per lane
+  const int grp = lane >> 3, sub = lane & 7;
+  float qreg[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) qreg[i] = s_q[sub * 16 + i];
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+
+  const int c_end = min(t_end, L);
+  for (int t = t_begin + warp * 4 + grp; t < c_end; t += 16) {
+    const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + t / c.page_tokens);
+    const int slot = t % c.page_tokens;
+    const uint4* kp = reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
+    const uint4* vp = reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
+    uint4 k0 = __ldg(kp), k1 = __ldg(kp + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
+    const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float2 kf = unpack_bf16x2(kw[i]);
+      sc += qreg[2 * i] * kf.x + qreg[2 * i + 1] * kf.y;
+    }
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    const float mn = fmaxf(m, sc);
+    const float cr = __expf(m - mn), p = __expf(sc - mn);
+    m = mn;
+    l = l * cr + p;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float2 vf = unpack_bf16x2(vw[i]);
+      acc[2 * i] = acc[2 * i] * cr + p * vf.x;
+      acc[2 * i + 1] = acc[2 * i + 1] * cr + p * vf.y;
+    }
+  }
+  // the new token (from smem), handled by warp 0 group 0 of the owning CTA
+  if (owns_new && warp == 0 && grp == 0) {
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sc += qreg[i] * s_k[sub * 16 + i];
+    sc += __shfl_xor_sync(0x000000ffu, sc, 1);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 2);
+    sc += __shfl_xor_sync(0x000000ffu, sc, 4);
+    const float mn = fmaxf(m, sc);
+    const float cr = __expf(m - mn), p = __expf(sc - mn);
+    m = mn;
+    l = l * cr + p;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = acc[i] * cr + p * s_v[sub * 16 + i];
+  }
+  // ---- merge the 4 token groups of a warp (lanes with equal `sub` hold the same dims)
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, m2);
+    const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn), c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
+      acc[i] = acc[i] * c1 + a2 * c2;
+    }
+    m = mn;
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s_acc[warp][sub * 16 + i] = acc[i];
+    if (sub == 0) { s_m[warp] = m; s_l[warp] = l; }
+  }
+  __syncthreads();
+  // ---- merge the 4 warps: thread d owns output dim d
+  float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+  float Lsum = 0.f, O = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float cw = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
+    Lsum += s_l[w] * cw;
+    O += s_acc[w][tid] * cw;
+  }
+  if (c.kv_splits == 1) {
+    c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(O / Lsum);
+    return;
+  }
+  // ---- cross-CTA combine: publish partial, last arriver reduces in fixed split order
+  float* sp = c.scratch + (((size_t)b * c.H + h) * c.kv_splits + split) * (HD + 2);
+  sp[tid] = O;
+  if (tid == 0) { sp[HD] = M; sp[HD + 1] = Lsum; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int old = atomicAdd(c.counters + b * c.H + h, 1);
+    s_last = (old == c.kv_splits - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* base = c.scratch + ((size_t)b * c.H + h) * c.kv_splits * (HD + 2);
+  float Mg = -INFINITY;
+  for (int s = 0; s < c.kv_splits; ++s) Mg = fmaxf(Mg, __ldcg(base + (size_t)s * (HD + 2) + HD));
+  float Lg = 0.f, Og = 0.f;
+  for (int s = 0; s < c.kv_splits; ++s) {
+    const float ms = __ldcg(base + (size_t)s * (HD + 2) + HD);
+    const float cw = (ms == -INFINITY) ? 0.f : __expf(ms - Mg);
+    Lg += __ldcg(base + (size_t)s * (HD + 2) + HD + 1) * cw;
+    Og += __ldcg(base + (size_t)s * (HD + 2) + tid) * cw;
+  }
+  c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(Og / Lg);
+  if (tid == 0) c.counters[b * c.H + h] = 0;  // ready for the next step / graph replay
+}
+
+// rope table owned by elementwise.cu
+const float* rope_cos_table();
+const float* rope_sin_table();
+
+int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
+  if (c.HD != 128) { set_error("attention_decode: head dim %d unsupported (128)", c.HD); return -1; }
+  if (rope_cos_table() == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_kernel, c, rope_cos_table(), rope_sin_table()));
+  return 0;
+}
+
+}  // namespace vcla

@@ -1,0 +1,519 @@
+// HBM-bound kernels of the VisualCLA path: normalisation, embedding / splice, RoPE + KV-cache append, the decode
+// consumers of the split-K partial sums, argmax, synthetic-weight generation and checkpoint repacking.
+// All are simple streaming kernels: 128-bit coalesced accesses where layouts allow, fp32 statistics.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <math.h>
+#include <vector>
+
+namespace vcla {
+
+static inline cudaLaunchConfig_t make_cfg(dim3 grid, dim3 block, size_t smem, cudaStream_t st, cudaLaunchAttribute* attr) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  return cfg;
+}
+#define VCLA_LAUNCH(kernel, grid, block, smem, st, ...)                         \
+  do {                                                                          \
+    cudaLaunchAttribute _attr[1];                                               \
+    cudaLaunchConfig_t _cfg = make_cfg(grid, block, smem, st, _attr);           \
+    VCLA_CUDA_OK(cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__));               \
+  } while (0)
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm: one CTA per row, row cached in smem, two-pass fp32 statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const float* x, int D, const float* __restrict__ w, const float* __restrict__ b,
+                                 float eps, bf16* __restrict__ y_bf16, float* y_f32) {
+  extern __shared__ float rowbuf[];
+  __shared__ float red[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const size_t row = blockIdx.x;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(xr + i);
+    *reinterpret_cast<float4*>(rowbuf + i) = v;
+    s += v.x + v.y + v.z + v.w;
+  }
+  const float mean = block_sum(s, red) / D;
+  float q = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(rowbuf + i);
+    float a = v.x - mean, bb = v.y - mean, cc = v.z - mean, dd = v.w - mean;
+    q += a * a + bb * bb + cc * cc + dd * dd;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / D + eps);
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(rowbuf + i);
+    float4 wv = *reinterpret_cast<const float4*>(w + i), bv = *reinterpret_cast<const float4*>(b + i);
+    float o0 = (v.x - mean) * rstd * wv.x + bv.x, o1 = (v.y - mean) * rstd * wv.y + bv.y;
+    float o2 = (v.z - mean) * rstd * wv.z + bv.z, o3 = (v.w - mean) * rstd * wv.w + bv.w;
+    if (y_bf16) *reinterpret_cast<uint2*>(y_bf16 + row * D + i) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    if (y_f32) *reinterpret_cast<float4*>(y_f32 + row * D + i) = make_float4(o0, o1, o2, o3);
+  }
+}
+int layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps, bf16* y_bf16, float* y_f32, cudaStream_t st) {
+  if (D % 4) { set_error("layernorm: D %% 4 != 0"); return -1; }
+  if (rows == 0) return 0;
+  VCLA_LAUNCH(layernorm_kernel, dim3(rows), dim3(D >= 2048 ? 256 : 128), (size_t)D * 4, st, x, D, w, b, eps, y_bf16, y_f32);
+  return 0;
+}
+
+__global__ void rmsnorm_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, float eps, bf16* __restrict__ y) {
+  extern __shared__ float rowbuf[];
+  __shared__ float red[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const size_t row = blockIdx.x;
+  const float* xr = x + row * D;
+  float q = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(xr + i);
+    *reinterpret_cast<float4*>(rowbuf + i) = v;
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / D + eps);
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(rowbuf + i);
+    float4 wv = *reinterpret_cast<const float4*>(w + i);
+    *reinterpret_cast<uint2*>(y + row * D + i) =
+        make_uint2(pack_bf16x2(v.x * rstd * wv.x, v.y * rstd * wv.y), pack_bf16x2(v.z * rstd * wv.z, v.w * rstd * wv.w));
+  }
+}
+int rmsnorm(const float* x, int rows, int D, const float* w, float eps, bf16* y, cudaStream_t st) {
+  if (D % 4) { set_error("rmsnorm: D %% 4 != 0"); return -1; }
+  if (rows == 0) return 0;
+  VCLA_LAUNCH(rmsnorm_kernel, dim3(rows), dim3(D >= 2048 ? 256 : 128), (size_t)D * 4, st, x, D, w, eps, y);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT front end
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ px, int B, int image, int patch, int kpad, bf16* __restrict__ out) {
+  // one CTA per patch row; k = c*P*P + ky*P + kx  (Conv2d weight (D,3,P,P) flattened)
+  const int g = image / patch;
+  const int prow = blockIdx.x;  // b*g*g + py*g + px
+  const int b = prow / (g * g), pp = prow % (g * g), py = pp / g, pxi = pp % g;
+  const int kreal = 3 * patch * patch;
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+    float v = 0.f;
+    if (k < kreal) {
+      int c = k / (patch * patch), r = k % (patch * patch), ky = r / patch, kx = r % patch;
+      v = to_f32<T>(px[(((size_t)b * 3 + c) * image + (py * patch + ky)) * image + (pxi * patch + kx)]);
+    }
+    out[(size_t)prow * kpad + k] = __float2bfloat16(v);
+  }
+}
+int im2col(const void* pixels, int dtype, int B, int image, int patch, int kpad, bf16* out, cudaStream_t st) {
+  const int g = image / patch;
+  dim3 grid(B * g * g), block(128);
+  if (dtype == 0) im2col_kernel<float><<<grid, block, 0, st>>>((const float*)pixels, B, image, patch, kpad, out);
+  else if (dtype == 1) im2col_kernel<__half><<<grid, block, 0, st>>>((const __half*)pixels, B, image, patch, kpad, out);
+  else if (dtype == 2) im2col_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)pixels, B, image, patch, kpad, out);
+  else { set_error("im2col: unknown pixel dtype %d", dtype); return -1; }
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void vit_cls_rows_kernel(float* hidden, int tokens, int D, const float* cls, const float* pos) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) hidden[(size_t)b * tokens * D + i] = cls[i] + pos[i];
+}
+int vit_cls_rows(float* hidden, int B, int tokens, int D, const float* cls, const float* pos, cudaStream_t st) {
+  vit_cls_rows_kernel<<<B, 256, 0, st>>>(hidden, tokens, D, cls, pos);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void broadcast_rows_kernel(const float* src, int rows, int D, float* dst_f32, bf16* dst_bf16) {
+  const int r = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float v = src[(size_t)r * D + i];
+    size_t o = ((size_t)b * rows + r) * D + i;
+    if (dst_f32) dst_f32[o] = v;
+    if (dst_bf16) dst_bf16[o] = __float2bfloat16(v);
+  }
+}
+int broadcast_rows(const float* src, int rows, int D, int B, float* dst_f32, bf16* dst_bf16, cudaStream_t st) {
+  broadcast_rows_kernel<<<dim3(rows, B), 256, 0, st>>>(src, rows, D, dst_f32, dst_bf16);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding gather / image splice
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, int T, int S, int D, const bf16* __restrict__ table,
+                                    int vocab, int mode, int nq, float* __restrict__ dst) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  long long id = ids[(size_t)b * T + t];
+  if (id < 0 || id >= vocab) id = 0;
+  const int pos = (mode == 1 && t >= 2) ? t + nq : t;
+  const bf16* src = table + (size_t)id * D;
+  float* d = dst + ((size_t)b * S + pos) * D;
+  for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+    uint4 v = *reinterpret_cast<const uint4*>(src + i);
+    float2 a = unpack_bf16x2(v.x), bb = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), e = unpack_bf16x2(v.w);
+    *reinterpret_cast<float4*>(d + i) = make_float4(a.x, a.y, bb.x, bb.y);
+    *reinterpret_cast<float4*>(d + i + 4) = make_float4(c.x, c.y, e.x, e.y);
+  }
+}
+int embed_tokens(const int64_t* ids, int B, int T, int S, int D, const bf16* table, int vocab, int mode, int nq, float* dst, cudaStream_t st) {
+  if (D % 8) { set_error("embed: D %% 8 != 0"); return -1; }
+  VCLA_LAUNCH(embed_tokens_kernel, dim3(T, B), dim3(128), 0, st, ids, T, S, D, table, vocab, mode, nq, dst);
+  return 0;
+}
+__global__ void embed_tokens_i32_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ dst) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x;
+  int id = ids[b];
+  if (id < 0 || id >= vocab) id = 0;
+  const bf16* src = table + (size_t)id * D;
+  float* d = dst + (size_t)b * D;
+  for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+    uint4 v = *reinterpret_cast<const uint4*>(src + i);
+    float2 a = unpack_bf16x2(v.x), bb = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), e = unpack_bf16x2(v.w);
+    *reinterpret_cast<float4*>(d + i) = make_float4(a.x, a.y, bb.x, bb.y);
+    *reinterpret_cast<float4*>(d + i + 4) = make_float4(c.x, c.y, e.x, e.y);
+  }
+}
+int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* dst, cudaStream_t st) {
+  VCLA_LAUNCH(embed_tokens_i32_kernel, dim3(B), dim3(256), 0, st, ids, D, table, vocab, dst);
+  return 0;
+}
+
+__global__ void scatter_image_rows_kernel(const float* __restrict__ img, int nq, int D, const int32_t* __restrict__ row_start, int S, float* __restrict__ dst) {
+  const int q = blockIdx.x, b = blockIdx.y;
+  const int rs = row_start[b];
+  if (rs < 0) return;  // this sample carries no image
+  const float4* s = reinterpret_cast<const float4*>(img + ((size_t)b * nq + q) * D);
+  float4* d = reinterpret_cast<float4*>(dst + ((size_t)b * S + rs + q) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) d[i] = s[i];
+}
+int scatter_image_rows(const float* img, int B, int nq, int D, const int32_t* row_start, int S, float* dst, cudaStream_t st) {
+  scatter_image_rows_kernel<<<dim3(nq, B), 256, 0, st>>>(img, nq, D, row_start, S, dst);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void gather_last_rows_kernel(const float* hidden, int S, int D, float* dst) {
+  const int b = blockIdx.x;
+  const float4* s = reinterpret_cast<const float4*>(hidden + ((size_t)b * S + (S - 1)) * D);
+  float4* d = reinterpret_cast<float4*>(dst + (size_t)b * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) d[i] = s[i];
+}
+int gather_last_rows(const float* hidden, int B, int S, int D, float* dst, cudaStream_t st) {
+  gather_last_rows_kernel<<<B, 256, 0, st>>>(hidden, S, D, dst);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE tables (fp32, computed once on the host the way HF does: HF:models/llama/modeling_llama.py:98-141)
+// ------------------------------------------------------------------------------------------------
+static float* g_rope_cos = nullptr;
+static float* g_rope_sin = nullptr;
+static int g_rope_pos = 0, g_rope_half = 0;
+static float g_rope_theta = 0.f;
+const float* rope_cos_table() { return g_rope_cos; }
+const float* rope_sin_table() { return g_rope_sin; }
+int rope_init(int max_pos, int head_dim, float theta) {
+  const int half = head_dim / 2;
+  if (g_rope_cos && g_rope_pos >= max_pos && g_rope_half == half && g_rope_theta == theta) return 0;
+  if (g_rope_cos) { cudaFree(g_rope_cos); cudaFree(g_rope_sin); g_rope_cos = g_rope_sin = nullptr; }
+  std::vector<float> hc((size_t)max_pos * half), hs((size_t)max_pos * half);
+  for (int i = 0; i < half; ++i) {
+    const float inv = 1.0f / powf(theta, (float)(2 * i) / (float)head_dim);
+    for (int p = 0; p < max_pos; ++p) {
+      const float f = (float)p * inv;
+      hc[(size_t)p * half + i] = (float)cos((double)f);
+      hs[(size_t)p * half + i] = (float)sin((double)f);
+    }
+  }
+  VCLA_CUDA_OK(cudaMalloc(&g_rope_cos, hc.size() * 4));
+  VCLA_CUDA_OK(cudaMalloc(&g_rope_sin, hs.size() * 4));
+  VCLA_CUDA_OK(cudaMemcpy(g_rope_cos, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+  VCLA_CUDA_OK(cudaMemcpy(g_rope_sin, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+  g_rope_pos = max_pos; g_rope_half = half; g_rope_theta = theta;
+  return 0;
+}
+
+// prefill: rotate q,k in place inside the fused [B*S, 3T] projection buffer; append k,v to the paged cache
+__global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int HD, const float* __restrict__ rc, const float* __restrict__ rs,
+                                      bf16* __restrict__ kv_pages, const int32_t* __restrict__ page_table, int pages_per_seq,
+                                      int page_tokens, const int32_t* __restrict__ seq_base) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int T = H * HD, half = HD / 2;
+  const int pos = (seq_base ? seq_base[b] : 0) + s;
+  bf16* row = qkv + ((size_t)b * S + s) * 3 * T;
+  const int page = page_table[(size_t)b * pages_per_seq + pos / page_tokens];
+  const int slot = pos % page_tokens;
+  // one thread per (head, i<half) pair
+  for (int idx = threadIdx.x; idx < H * half; idx += blockDim.x) {
+    const int h = idx / half, i = idx % half;
+    const float c = rc[(size_t)pos * half + i], sn = rs[(size_t)pos * half + i];
+    bf16* q = row + h * HD;
+    bf16* k = row + T + h * HD;
+    const bf16* v = row + 2 * T + h * HD;
+    float q1 = __bfloat162float(q[i]), q2 = __bfloat162float(q[i + half]);
+    float k1 = __bfloat162float(k[i]), k2 = __bfloat162float(k[i + half]);
+    const bf16 qo1 = __float2bfloat16(q1 * c - q2 * sn), qo2 = __float2bfloat16(q2 * c + q1 * sn);
+    const bf16 ko1 = __float2bfloat16(k1 * c - k2 * sn), ko2 = __float2bfloat16(k2 * c + k1 * sn);
+    q[i] = qo1; q[i + half] = qo2;
+    k[i] = ko1; k[i + half] = ko2;
+    bf16* kd = kv_pages + ((((size_t)page * 2 + 0) * H + h) * page_tokens + slot) * HD;
+    bf16* vd = kv_pages + ((((size_t)page * 2 + 1) * H + h) * page_tokens + slot) * HD;
+    kd[i] = ko1; kd[i + half] = ko2;
+    vd[i] = v[i]; vd[i + half] = v[i + half];
+  }
+}
+int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table, int pages_per_seq,
+                   int page_tokens, const int32_t* seq_base, cudaStream_t st) {
+  (void)theta;
+  if (!g_rope_cos) { set_error("rope table not initialised"); return -1; }
+  VCLA_LAUNCH(rope_and_cache_kernel, dim3(S, B), dim3(256), 0, st, qkv, S, H, HD, (const float*)g_rope_cos, (const float*)g_rope_sin,
+              kv_pages, page_table, pages_per_seq, page_tokens, seq_base);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode consumers of split-K partial sums
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows, float* __restrict__ resid, int D,
+                                      const float* __restrict__ w, float eps, bf16* __restrict__ xn) {
+  extern __shared__ float rowbuf[];
+  __shared__ float red[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x;
+  float q = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<const float4*>(resid + (size_t)b * D + i);
+    if (partial) {
+      for (int s = 0; s < splits; ++s) {
+        float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * ws_rows + b) * D + i);
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+      }
+      *reinterpret_cast<float4*>(resid + (size_t)b * D + i) = v;
+    }
+    *reinterpret_cast<float4*>(rowbuf + i) = v;
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / D + eps);
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(rowbuf + i);
+    float4 wv = *reinterpret_cast<const float4*>(w + i);
+    *reinterpret_cast<uint2*>(xn + (size_t)b * D + i) =
+        make_uint2(pack_bf16x2(v.x * rstd * wv.x, v.y * rstd * wv.y), pack_bf16x2(v.z * rstd * wv.z, v.w * rstd * wv.w));
+  }
+}
+int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, int B, int D, const float* w, float eps, bf16* xn, cudaStream_t st) {
+  VCLA_LAUNCH(dec_resid_norm_kernel, dim3(B), dim3(D >= 2048 ? 512 : 128), (size_t)D * 4, st, partial, splits, ws_rows, resid, D, w, eps, xn);
+  return 0;
+}
+
+__global__ void dec_silu_mul_kernel(const float* __restrict__ partial, int splits, int ws_rows, int F, bf16* __restrict__ h) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= F) return;
+  const int gi = (j >> 5) * 64 + (j & 31);
+  float g = 0.f, u = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* row = partial + ((size_t)s * ws_rows + b) * (size_t)(2 * F);
+    g += row[gi];
+    u += row[gi + 32];
+  }
+  h[(size_t)b * F + j] = __float2bfloat16(g / (1.f + __expf(-g)) * u);
+}
+int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st) {
+  VCLA_LAUNCH(dec_silu_mul_kernel, dim3((F + 255) / 256, B), dim3(256), 0, st, partial, splits, ws_rows, F, h);
+  return 0;
+}
+
+// logits + argmax: stage 1 per (vocab chunk, b) -> candidate ; stage 2 per b
+constexpr int kArgChunks = 32;
+__global__ void dec_logits_stage1(const float* __restrict__ partial, int splits, int ws_rows, int ldp, int V, float* __restrict__ logits,
+                                  int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.y, ch = blockIdx.x;
+  const int per = (V + kArgChunks - 1) / kArgChunks;
+  const int v0 = ch * per, v1 = min(V, v0 + per);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    float x = 0.f;
+    for (int s = 0; s < splits; ++s) x += partial[((size_t)s * ws_rows + b) * (size_t)ldp + v];
+    if (logits) logits[(size_t)b * ld_logits + v] = x;
+    if (x > best) { best = x; bi = v; }   // strided order: smaller index kept on ties via the reduction below
+  }
+  // warp + block reduce, ties -> smallest index
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? sv[lane] : -INFINITY;
+    bi = lane < nw ? si[lane] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { cand_val[b * kArgChunks + ch] = best; cand_idx[b * kArgChunks + ch] = bi; }
+  }
+}
+__global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x, lane = threadIdx.x;
+  float best = cand_val[b * kArgChunks + lane];
+  int bi = cand_idx[b * kArgChunks + lane];
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) tok[b] = bi;
+}
+static float* g_cand_val = nullptr;
+static int* g_cand_idx = nullptr;
+static int g_cand_cap = 0;
+int argmax_scratch_init(int max_batch) {
+  if (g_cand_cap >= max_batch) return 0;
+  if (g_cand_val) { cudaFree(g_cand_val); cudaFree(g_cand_idx); }
+  VCLA_CUDA_OK(cudaMalloc(&g_cand_val, (size_t)max_batch * kArgChunks * 4));
+  VCLA_CUDA_OK(cudaMalloc(&g_cand_idx, (size_t)max_batch * kArgChunks * 4));
+  g_cand_cap = max_batch;
+  return 0;
+}
+int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok, cudaStream_t st) {
+  if (g_cand_cap < B) { set_error("argmax scratch too small (%d < %d)", g_cand_cap, B); return -1; }
+  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx);
+  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok);
+  return 0;
+}
+
+__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) seq_len[b] += by;
+}
+int advance_seq(int32_t* seq_len, int B, int by, cudaStream_t st) {
+  VCLA_LAUNCH(advance_seq_kernel, dim3((B + 63) / 64), dim3(64), 0, st, seq_len, B, by);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: synthetic generator (bit-identical to oracle.hash_normal_bf16) and checkpoint repacking
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__global__ void fill_hash_normal_kernel(bf16* dst_bf16, float* dst_f32, int64_t n, uint32_t seed, float mul, float offset) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = fmix32((uint32_t)i * 0x9E3779B1u + seed);
+    const uint32_t b = fmix32(a ^ 0x7F4A7C15u);
+    const int tot = (int)(a & 0xFFFFu) + (int)(a >> 16) + (int)(b & 0xFFFFu) + (int)(b >> 16) - 131070;
+    const float v = __fadd_rn(__fmul_rn((float)tot, mul), offset);   // no FMA contraction: must match numpy bit for bit
+    const bf16 r = __float2bfloat16(v);
+    if (dst_bf16) dst_bf16[i] = r;
+    if (dst_f32) dst_f32[i] = __bfloat162float(r);
+  }
+}
+int fill_hash_normal(bf16* dst_bf16, float* dst_f32, int64_t n, uint32_t seed, float mul, float offset, cudaStream_t st) {
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fill_hash_normal_kernel<<<(int)blocks, 256, 0, st>>>(dst_bf16, dst_f32, n, seed, mul, offset);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, typename O>
+__global__ void convert_kernel(const T* src, int64_t n, O* dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = to_f32<T>(src[i]);
+    if constexpr (sizeof(O) == 2) dst[i] = __float2bfloat16(v);
+    else dst[i] = v;
+  }
+}
+template <typename O>
+static int convert_any(const void* src, int dtype, int64_t n, O* dst, cudaStream_t st) {
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks == 0) return 0;
+  if (dtype == 0) convert_kernel<float, O><<<(int)blocks, 256, 0, st>>>((const float*)src, n, dst);
+  else if (dtype == 1) convert_kernel<__half, O><<<(int)blocks, 256, 0, st>>>((const __half*)src, n, dst);
+  else if (dtype == 2) convert_kernel<bf16, O><<<(int)blocks, 256, 0, st>>>((const bf16*)src, n, dst);
+  else { set_error("convert: unknown dtype %d", dtype); return -1; }
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int convert_to_bf16(const void* src, int dtype, int64_t n, bf16* dst, cudaStream_t st) { return convert_any<bf16>(src, dtype, n, dst, st); }
+int convert_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st) { return convert_any<float>(src, dtype, n, dst, st); }
+
+__global__ void copy_rows_bf16_kernel(const bf16* src, int cols, bf16* dst, int ld) {
+  const size_t r = blockIdx.x;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) dst[r * ld + i] = (i < cols) ? src[r * cols + i] : __float2bfloat16(0.f);
+}
+int copy_rows_bf16(const bf16* src, int rows, int cols, bf16* dst, int ld, cudaStream_t st) {
+  if (rows == 0) return 0;
+  copy_rows_bf16_kernel<<<rows, 256, 0, st>>>(src, cols, dst, ld);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+__global__ void interleave_rows32_kernel(const bf16* src, int cols, int which, bf16* dst) {
+  const size_t j = blockIdx.x;
+  const size_t r = (j >> 5) * 64 + (size_t)which * 32 + (j & 31);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) dst[r * cols + i] = src[j * cols + i];
+}
+int interleave_rows32(const bf16* src, int rows, int cols, int which, bf16* dst, cudaStream_t st) {
+  interleave_rows32_kernel<<<rows, 256, 0, st>>>(src, cols, which, dst);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vcla

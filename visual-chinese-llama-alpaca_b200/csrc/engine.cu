@@ -1,0 +1,777 @@
+// Engine behind the C ABI (include/vcla.h): device arenas, weight registry / repacking, and the orchestration of
+// the three phases of the path -- vision encode, prefill, decode step (CUDA-graph captured).
+#include "../../include/vcla.h"
+#include "kernels.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace vcla {
+int rope_init(int max_pos, int head_dim, float theta);
+int argmax_scratch_init(int max_batch);
+}  // namespace vcla
+
+using namespace vcla;
+
+namespace {
+
+enum SlotKind { SLOT_MAT = 0, SLOT_VEC = 1 };
+enum SlotLayout { LAY_PLAIN = 0, LAY_INTERLEAVE32 = 1 };
+
+struct Slot {
+  std::string name;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int ndim = 0;
+  int kind = SLOT_MAT;
+  int layout = LAY_PLAIN;
+  int which = 0;           // interleave: 0 gate, 1 up
+  int64_t rows = 0, cols = 0;  // 2D view of the logical tensor
+  void* dst = nullptr;     // storage (bf16 for MAT, f32 for VEC) at the slot's first row
+  int ld = 0;              // storage row pitch (elements) for MAT
+  void* dst2 = nullptr;    // optional second copy (resampler k/v also live in the all-layer KV weight)
+  float std = 0.f, mean = 0.f;
+};
+
+struct VisionLayer {
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *bqkv, *bo, *b1, *b2;
+  bf16 *wqkv, *wo, *w1, *w2;
+};
+struct ResamplerLayer {
+  bf16 *wqkv, *wo, *wi, *wo2;
+  float *bqkv, *bo, *ln1_w, *ln1_b, *bi, *bo2, *ln2_w, *ln2_b;
+};
+struct TextLayer {
+  float *ln1, *ln2;
+  bf16 *wqkv, *wo, *wgu, *wd;
+  bf16* kv;  // this layer's pages
+};
+
+struct GraphKey {
+  int B; const void* tok_in; const void* logits; const void* tok_out;
+  bool operator<(const GraphKey& o) const {
+    if (B != o.B) return B < o.B;
+    if (tok_in != o.tok_in) return tok_in < o.tok_in;
+    if (logits != o.logits) return logits < o.logits;
+    return tok_out < o.tok_out;
+  }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+uint32_t fnv1a32(const char* s) {
+  uint32_t h = 0x811C9DC5u;
+  for (; *s; ++s) { h ^= (uint8_t)*s; h *= 0x01000193u; }
+  return h;
+}
+
+}  // namespace
+
+struct vcla_ctx {
+  vcla_config cfg;
+  int v_tokens = 0, kpatch = 0, kpad = 0, hd_t = 0;
+  // arenas
+  uint8_t* w_arena = nullptr; size_t w_bytes = 0, w_off = 0;
+  uint8_t* a_arena = nullptr; size_t a_bytes = 0, a_off = 0;
+  bf16* kv_arena = nullptr; size_t kv_bytes = 0;
+  std::vector<Slot> slots;
+  std::map<std::string, int> slot_index;
+  // vision weights
+  bf16* patch_w = nullptr; float *cls = nullptr, *pos = nullptr, *pre_w = nullptr, *pre_b = nullptr, *post_w = nullptr, *post_b = nullptr;
+  std::vector<VisionLayer> vl;
+  // resampler
+  float* rq = nullptr; bf16* r_wkv_all = nullptr; float* r_bkv_all = nullptr;
+  std::vector<ResamplerLayer> rl;
+  bf16* proj_w = nullptr; float* proj_b = nullptr;
+  // text
+  bf16 *embed = nullptr, *lm_head = nullptr; float* final_norm = nullptr;
+  std::vector<TextLayer> tl;
+  // kv cache
+  int pages_per_seq = 0, page_tokens = 64, total_pages = 0;
+  size_t kv_layer_elems = 0;
+  int32_t *page_table = nullptr, *seq_len = nullptr, *img_row_default = nullptr;
+  // vision activations
+  bf16 *v_im2col = nullptr, *v_norm = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_ffn = nullptr;
+  float *v_hidden = nullptr, *v_postln_f32 = nullptr;
+  float *r_hidden = nullptr, *img_embeds = nullptr;
+  bf16 *r_hidden_bf16 = nullptr, *r_qkv = nullptr, *r_kvimg = nullptr, *r_ctx = nullptr, *r_ffn = nullptr;
+  // prefill activations
+  float* resid = nullptr; bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hmid = nullptr;
+  // decode activations
+  float* d_resid = nullptr; bf16 *d_xn = nullptr, *d_attn = nullptr, *d_h = nullptr;
+  float *ws_qkv = nullptr, *ws_o = nullptr, *ws_gu = nullptr, *ws_d = nullptr, *ws_lm = nullptr;
+  float* attn_scratch = nullptr; int32_t* attn_counters = nullptr;
+  int32_t* d_tok = nullptr;
+  int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
+  // graphs
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int64_t> graph_launches;
+  int64_t launches = 0;
+  void* staging = nullptr; size_t staging_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+T* w_alloc(vcla_ctx* c, size_t n) {
+  size_t bytes = align_up(n * sizeof(T), 256);
+  if (c->w_arena == nullptr) { c->w_off += bytes; return nullptr; }   // sizing pass
+  T* p = reinterpret_cast<T*>(c->w_arena + c->w_off);
+  c->w_off += bytes;
+  return p;
+}
+template <typename T>
+T* a_alloc(vcla_ctx* c, size_t n) {
+  size_t bytes = align_up(n * sizeof(T), 1024);
+  if (c->a_arena == nullptr) { c->a_off += bytes; return nullptr; }
+  T* p = reinterpret_cast<T*>(c->a_arena + c->a_off);
+  c->a_off += bytes;
+  return p;
+}
+
+void add_slot(vcla_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, int kind, void* dst, int ld, float std_,
+              float mean_, int layout = LAY_PLAIN, int which = 0, void* dst2 = nullptr) {
+  if (c->w_arena == nullptr) return;  // sizing pass: no registry
+  Slot s;
+  s.name = name; s.kind = kind; s.layout = layout; s.which = which; s.dst = dst; s.ld = ld; s.dst2 = dst2; s.std = std_; s.mean = mean_;
+  s.ndim = (int)shape.size();
+  int i = 0; int64_t numel = 1;
+  for (int64_t d : shape) { s.shape[i++] = d; numel *= d; }
+  s.rows = shape.size() ? *shape.begin() : 1;
+  s.cols = s.rows ? numel / s.rows : 0;
+  if (kind == SLOT_VEC) { s.rows = 1; s.cols = numel; }
+  c->slot_index[name] = (int)c->slots.size();
+  c->slots.push_back(s);
+}
+
+// Lays out every weight in the arena.  Called twice: once with w_arena == nullptr to size, once to assign.
+// std / mean per tensor follow oracle/visualcla_oracle.py:weight_specs exactly.
+void layout_weights(vcla_ctx* c) {
+  const vcla_config& g = c->cfg;
+  c->w_off = 0;
+  const int D = g.v_hidden, Fv = g.v_ffn;
+  const std::string vp = "vision_model.vision_model.";
+  c->cls = w_alloc<float>(c, D);
+  add_slot(c, vp + "embeddings.class_embedding", {D}, SLOT_VEC, c->cls, 0, 1.0f, 0.f);
+  c->patch_w = w_alloc<bf16>(c, (size_t)D * c->kpad);
+  add_slot(c, vp + "embeddings.patch_embedding.weight", {D, 3, g.v_patch, g.v_patch}, SLOT_MAT, c->patch_w, c->kpad, 1.0f / sqrtf((float)c->kpatch), 0.f);
+  c->pos = w_alloc<float>(c, (size_t)c->v_tokens * D);
+  add_slot(c, vp + "embeddings.position_embedding.weight", {c->v_tokens, D}, SLOT_VEC, c->pos, 0, 0.5f, 0.f);
+  c->pre_w = w_alloc<float>(c, D); add_slot(c, vp + "pre_layrnorm.weight", {D}, SLOT_VEC, c->pre_w, 0, 0.1f, 1.f);
+  c->pre_b = w_alloc<float>(c, D); add_slot(c, vp + "pre_layrnorm.bias", {D}, SLOT_VEC, c->pre_b, 0, 0.1f, 0.f);
+  c->vl.resize(g.v_layers);
+  for (int i = 0; i < g.v_layers; ++i) {
+    VisionLayer& L = c->vl[i];
+    const std::string lp = vp + "encoder.layers." + std::to_string(i) + ".";
+    L.ln1_w = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm1.weight", {D}, SLOT_VEC, L.ln1_w, 0, 0.1f, 1.f);
+    L.ln1_b = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm1.bias", {D}, SLOT_VEC, L.ln1_b, 0, 0.1f, 0.f);
+    L.ln2_w = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm2.weight", {D}, SLOT_VEC, L.ln2_w, 0, 0.1f, 1.f);
+    L.ln2_b = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm2.bias", {D}, SLOT_VEC, L.ln2_b, 0, 0.1f, 0.f);
+    L.wqkv = w_alloc<bf16>(c, (size_t)3 * D * D);
+    L.bqkv = w_alloc<float>(c, 3 * D);
+    const char* pr[3] = {"q_proj", "k_proj", "v_proj"};
+    for (int j = 0; j < 3; ++j) {
+      add_slot(c, lp + "self_attn." + pr[j] + ".weight", {D, D}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)j * D * D : nullptr, D, 1.5f / sqrtf((float)D), 0.f);
+      add_slot(c, lp + "self_attn." + pr[j] + ".bias", {D}, SLOT_VEC, L.bqkv ? L.bqkv + j * D : nullptr, 0, 0.1f, 0.f);
+    }
+    L.wo = w_alloc<bf16>(c, (size_t)D * D); add_slot(c, lp + "self_attn.out_proj.weight", {D, D}, SLOT_MAT, L.wo, D, 0.5f / sqrtf((float)D), 0.f);
+    L.bo = w_alloc<float>(c, D); add_slot(c, lp + "self_attn.out_proj.bias", {D}, SLOT_VEC, L.bo, 0, 0.05f, 0.f);
+    L.w1 = w_alloc<bf16>(c, (size_t)Fv * D); add_slot(c, lp + "mlp.fc1.weight", {Fv, D}, SLOT_MAT, L.w1, D, 1.0f / sqrtf((float)D), 0.f);
+    L.b1 = w_alloc<float>(c, Fv); add_slot(c, lp + "mlp.fc1.bias", {Fv}, SLOT_VEC, L.b1, 0, 0.1f, 0.f);
+    L.w2 = w_alloc<bf16>(c, (size_t)D * Fv); add_slot(c, lp + "mlp.fc2.weight", {D, Fv}, SLOT_MAT, L.w2, Fv, 0.5f / sqrtf((float)Fv), 0.f);
+    L.b2 = w_alloc<float>(c, D); add_slot(c, lp + "mlp.fc2.bias", {D}, SLOT_VEC, L.b2, 0, 0.05f, 0.f);
+  }
+  c->post_w = w_alloc<float>(c, D); add_slot(c, vp + "post_layernorm.weight", {D}, SLOT_VEC, c->post_w, 0, 0.1f, 1.f);
+  c->post_b = w_alloc<float>(c, D); add_slot(c, vp + "post_layernorm.bias", {D}, SLOT_VEC, c->post_b, 0, 0.1f, 0.f);
+
+  const int R = g.r_hidden, Fr = g.r_ffn, Q = g.r_queries, RL = g.r_layers;
+  const std::string rp = "visual_resampler.";
+  c->rq = w_alloc<float>(c, (size_t)Q * R); add_slot(c, rp + "query_embeddding", {1, Q, R}, SLOT_VEC, c->rq, 0, 1.0f, 0.f);
+  c->r_wkv_all = w_alloc<bf16>(c, (size_t)RL * 2 * R * R);
+  c->r_bkv_all = w_alloc<float>(c, (size_t)RL * 2 * R);
+  c->rl.resize(RL);
+  for (int i = 0; i < RL; ++i) {
+    ResamplerLayer& L = c->rl[i];
+    const std::string lp = rp + "encoder.layer." + std::to_string(i) + ".";
+    L.wqkv = w_alloc<bf16>(c, (size_t)3 * R * R);
+    L.bqkv = w_alloc<float>(c, 3 * R);
+    const char* pr[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; ++j) {
+      // key/value additionally live in the all-layer [RL*2R, R] matrix used for the layer-invariant image rows
+      void* d2w = (j > 0 && c->r_wkv_all) ? (void*)(c->r_wkv_all + ((size_t)i * 2 + (j - 1)) * R * R) : nullptr;
+      void* d2b = (j > 0 && c->r_bkv_all) ? (void*)(c->r_bkv_all + ((size_t)i * 2 + (j - 1)) * R) : nullptr;
+      add_slot(c, lp + "crossattention.self." + pr[j] + ".weight", {R, R}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)j * R * R : nullptr, R, 1.5f / sqrtf((float)R), 0.f, LAY_PLAIN, 0, d2w);
+      add_slot(c, lp + "crossattention.self." + pr[j] + ".bias", {R}, SLOT_VEC, L.bqkv ? L.bqkv + j * R : nullptr, 0, 0.1f, 0.f, LAY_PLAIN, 0, d2b);
+    }
+    L.wo = w_alloc<bf16>(c, (size_t)R * R); add_slot(c, lp + "crossattention.output.dense.weight", {R, R}, SLOT_MAT, L.wo, R, 1.0f / sqrtf((float)R), 0.f);
+    L.bo = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.dense.bias", {R}, SLOT_VEC, L.bo, 0, 0.05f, 0.f);
+    L.ln1_w = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.LayerNorm.weight", {R}, SLOT_VEC, L.ln1_w, 0, 0.1f, 1.f);
+    L.ln1_b = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.LayerNorm.bias", {R}, SLOT_VEC, L.ln1_b, 0, 0.1f, 0.f);
+    L.wi = w_alloc<bf16>(c, (size_t)Fr * R); add_slot(c, lp + "intermediate.dense.weight", {Fr, R}, SLOT_MAT, L.wi, R, 1.0f / sqrtf((float)R), 0.f);
+    L.bi = w_alloc<float>(c, Fr); add_slot(c, lp + "intermediate.dense.bias", {Fr}, SLOT_VEC, L.bi, 0, 0.1f, 0.f);
+    L.wo2 = w_alloc<bf16>(c, (size_t)R * Fr); add_slot(c, lp + "output.dense.weight", {R, Fr}, SLOT_MAT, L.wo2, Fr, 1.0f / sqrtf((float)Fr), 0.f);
+    L.bo2 = w_alloc<float>(c, R); add_slot(c, lp + "output.dense.bias", {R}, SLOT_VEC, L.bo2, 0, 0.05f, 0.f);
+    L.ln2_w = w_alloc<float>(c, R); add_slot(c, lp + "output.LayerNorm.weight", {R}, SLOT_VEC, L.ln2_w, 0, 0.1f, 1.f);
+    L.ln2_b = w_alloc<float>(c, R); add_slot(c, lp + "output.LayerNorm.bias", {R}, SLOT_VEC, L.ln2_b, 0, 0.1f, 0.f);
+  }
+  const int T = g.t_hidden, Ft = g.t_ffn, V = g.t_vocab, TL = g.t_layers;
+  c->proj_w = w_alloc<bf16>(c, (size_t)T * R); add_slot(c, "image_projection_layer.weight", {T, R}, SLOT_MAT, c->proj_w, R, 1.0f / sqrtf((float)R), 0.f);
+  c->proj_b = w_alloc<float>(c, T); add_slot(c, "image_projection_layer.bias", {T}, SLOT_VEC, c->proj_b, 0, 0.1f, 0.f);
+
+  const std::string tp = "text_model.model.";
+  const float res_gain = 1.0f / sqrtf(2.0f * (float)TL);
+  c->embed = w_alloc<bf16>(c, (size_t)V * T); add_slot(c, tp + "embed_tokens.weight", {V, T}, SLOT_MAT, c->embed, T, 1.0f, 0.f);
+  c->tl.resize(TL);
+  for (int i = 0; i < TL; ++i) {
+    TextLayer& L = c->tl[i];
+    const std::string lp = tp + "layers." + std::to_string(i) + ".";
+    L.ln1 = w_alloc<float>(c, T); add_slot(c, lp + "input_layernorm.weight", {T}, SLOT_VEC, L.ln1, 0, 0.1f, 1.f);
+    L.ln2 = w_alloc<float>(c, T); add_slot(c, lp + "post_attention_layernorm.weight", {T}, SLOT_VEC, L.ln2, 0, 0.1f, 1.f);
+    L.wqkv = w_alloc<bf16>(c, (size_t)3 * T * T);
+    add_slot(c, lp + "self_attn.q_proj.weight", {T, T}, SLOT_MAT, L.wqkv, T, 1.5f / sqrtf((float)T), 0.f);
+    add_slot(c, lp + "self_attn.k_proj.weight", {T, T}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)T * T : nullptr, T, 1.5f / sqrtf((float)T), 0.f);
+    add_slot(c, lp + "self_attn.v_proj.weight", {T, T}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)2 * T * T : nullptr, T, 1.0f / sqrtf((float)T), 0.f);
+    L.wo = w_alloc<bf16>(c, (size_t)T * T); add_slot(c, lp + "self_attn.o_proj.weight", {T, T}, SLOT_MAT, L.wo, T, res_gain * 2.0f / sqrtf((float)T), 0.f);
+    L.wgu = w_alloc<bf16>(c, (size_t)2 * Ft * T);
+    add_slot(c, lp + "mlp.gate_proj.weight", {Ft, T}, SLOT_MAT, L.wgu, T, 1.0f / sqrtf((float)T), 0.f, LAY_INTERLEAVE32, 0);
+    add_slot(c, lp + "mlp.up_proj.weight", {Ft, T}, SLOT_MAT, L.wgu, T, 1.0f / sqrtf((float)T), 0.f, LAY_INTERLEAVE32, 1);
+    L.wd = w_alloc<bf16>(c, (size_t)T * Ft); add_slot(c, lp + "mlp.down_proj.weight", {T, Ft}, SLOT_MAT, L.wd, Ft, res_gain * 4.0f / sqrtf((float)Ft), 0.f);
+  }
+  c->final_norm = w_alloc<float>(c, T); add_slot(c, tp + "norm.weight", {T}, SLOT_VEC, c->final_norm, 0, 0.1f, 1.f);
+  c->lm_head = w_alloc<bf16>(c, (size_t)V * T); add_slot(c, "text_model.lm_head.weight", {V, T}, SLOT_MAT, c->lm_head, T, 4.0f / sqrtf((float)T), 0.f);
+}
+
+void layout_activations(vcla_ctx* c) {
+  const vcla_config& g = c->cfg;
+  c->a_off = 0;
+  const size_t Bv = g.max_batch, VT = (size_t)Bv * c->v_tokens, D = g.v_hidden, gg = (size_t)(c->v_tokens - 1);
+  c->v_im2col = a_alloc<bf16>(c, Bv * gg * c->kpad);
+  c->v_hidden = a_alloc<float>(c, VT * D);
+  c->v_norm = a_alloc<bf16>(c, VT * D);
+  c->v_qkv = a_alloc<bf16>(c, VT * 3 * D);
+  c->v_attn = a_alloc<bf16>(c, VT * D);
+  c->v_ffn = a_alloc<bf16>(c, VT * g.v_ffn);
+  c->v_postln_f32 = a_alloc<float>(c, VT * D);
+  const size_t RQ = (size_t)Bv * g.r_queries, R = g.r_hidden;
+  c->r_hidden = a_alloc<float>(c, RQ * R);
+  c->r_hidden_bf16 = a_alloc<bf16>(c, RQ * R);
+  c->r_qkv = a_alloc<bf16>(c, RQ * 3 * R);
+  c->r_kvimg = a_alloc<bf16>(c, VT * (size_t)g.r_layers * 2 * R);
+  c->r_ctx = a_alloc<bf16>(c, RQ * R);
+  c->r_ffn = a_alloc<bf16>(c, RQ * g.r_ffn);
+  c->img_embeds = a_alloc<float>(c, RQ * g.t_hidden);
+  const size_t Tk = g.max_prefill_tokens, T = g.t_hidden, F = g.t_ffn;
+  c->resid = a_alloc<float>(c, Tk * T);
+  c->xn = a_alloc<bf16>(c, Tk * T);
+  c->qkv = a_alloc<bf16>(c, Tk * 3 * T);
+  c->attn = a_alloc<bf16>(c, Tk * T);
+  c->hmid = a_alloc<bf16>(c, Tk * F);
+  const size_t Bp = 64;  // decode operand rows (batch is processed in chunks of <= 64)
+  c->d_resid = a_alloc<float>(c, Bp * T);
+  c->d_xn = a_alloc<bf16>(c, Bp * T);
+  c->d_attn = a_alloc<bf16>(c, Bp * T);
+  c->d_h = a_alloc<bf16>(c, Bp * F);
+  c->ws_qkv = a_alloc<float>(c, (size_t)c->sp_qkv * Bp * 3 * T);
+  c->ws_o = a_alloc<float>(c, (size_t)c->sp_o * Bp * T);
+  c->ws_gu = a_alloc<float>(c, (size_t)c->sp_gu * Bp * 2 * F);
+  c->ws_d = a_alloc<float>(c, (size_t)c->sp_d * Bp * T);
+  c->ws_lm = a_alloc<float>(c, (size_t)c->sp_lm * Bp * g.t_vocab);
+  c->attn_scratch = a_alloc<float>(c, (size_t)Bp * g.t_heads * c->kv_splits * (128 + 2));
+  c->attn_counters = a_alloc<int32_t>(c, (size_t)Bp * g.t_heads);
+  c->d_tok = a_alloc<int32_t>(c, Bp);
+  c->page_table = a_alloc<int32_t>(c, (size_t)g.max_batch * c->pages_per_seq);
+  c->seq_len = a_alloc<int32_t>(c, g.max_batch);
+  c->img_row_default = a_alloc<int32_t>(c, g.max_batch);
+}
+
+// choose split-K factors so every decode GEMM launches ~2 waves of 2-CTA/SM work with >= 8 k-blocks per split
+int pick_splits(int n_out, int K) {
+  const int tiles = (n_out + 127) / 128;
+  const int kb = (K + 63) / 64;
+  const int target = 2 * 148 * 2;
+  int s = (target + tiles - 1) / tiles;
+  int max_s = kb / 8; if (max_s < 1) max_s = 1;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  // make it realisable: every split non-empty with equal kb_per_split
+  int per = (kb + s - 1) / s;
+  s = (kb + per - 1) / per;
+  return s;
+}
+
+int count(vcla_ctx* c, int n = 1) { c->launches += n; return 0; }
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* vcla_last_error(void) { return get_error(); }
+const char* vcla_version(void) { return "vcla-b200 0.1 (sm_100a, tcgen05/TMA)"; }
+void vcla_set_pdl(int on) { set_pdl(on != 0); }
+
+int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
+  if (!cfg || !out) { set_error("vcla_create: null argument"); return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("vcla_create: no CUDA device (this library has no CPU fallback)");
+    return -1;
+  }
+  vcla_ctx* c = new vcla_ctx();
+  c->cfg = *cfg;
+  vcla_config& g = c->cfg;
+  if (g.page_tokens <= 0) g.page_tokens = 64;
+  auto bad = [&](const char* why) { set_error("vcla_create: %s", why); delete c; return -1; };
+  if (g.t_hidden % g.t_heads || g.t_hidden / g.t_heads != 128) return bad("LLaMA head_dim must be 128");
+  if (g.v_hidden % g.v_heads || g.v_hidden / g.v_heads != 64) return bad("ViT head_dim must be 64");
+  if (g.r_hidden % g.r_heads || g.r_hidden / g.r_heads != 64) return bad("Resampler head_dim must be 64");
+  if (g.t_ffn % 32) return bad("LLaMA ffn must be a multiple of 32");
+  if (g.v_hidden % 8 || g.r_hidden % 8 || g.t_hidden % 8 || g.v_ffn % 8 || g.r_ffn % 8 || g.t_ffn % 8) return bad("hidden sizes must be multiples of 8");
+  if (g.v_image % g.v_patch) return bad("image size must be a multiple of the patch size");
+  if (g.max_batch < 1 || g.max_seq < 1 || g.max_prefill_tokens < 1) return bad("capacities must be positive");
+  if (g.max_seq > 1 << 20) return bad("max_seq too large");
+  c->v_tokens = (g.v_image / g.v_patch) * (g.v_image / g.v_patch) + 1;
+  c->kpatch = 3 * g.v_patch * g.v_patch;
+  c->kpad = (c->kpatch + 63) / 64 * 64;
+  c->hd_t = 128;
+  c->page_tokens = g.page_tokens;
+  c->pages_per_seq = (g.max_seq + c->page_tokens - 1) / c->page_tokens;
+  c->total_pages = c->pages_per_seq * g.max_batch;
+  c->sp_qkv = pick_splits(3 * g.t_hidden, g.t_hidden);
+  c->sp_o = pick_splits(g.t_hidden, g.t_hidden);
+  c->sp_gu = pick_splits(2 * g.t_ffn, g.t_hidden);
+  c->sp_d = pick_splits(g.t_hidden, g.t_ffn);
+  c->sp_lm = pick_splits(g.t_vocab, g.t_hidden);
+  c->kv_splits = g.max_seq >= 1024 ? 8 : (g.max_seq >= 256 ? 4 : 1);
+
+  if (gemm_init()) { delete c; return -1; }
+  // sizing passes
+  layout_weights(c); c->w_bytes = c->w_off;
+  layout_activations(c); c->a_bytes = c->a_off;
+  c->kv_layer_elems = (size_t)c->total_pages * 2 * g.t_heads * c->page_tokens * 128;
+  c->kv_bytes = c->kv_layer_elems * g.t_layers * sizeof(bf16);
+  cudaError_t e;
+  if ((e = cudaMalloc(&c->w_arena, c->w_bytes)) != cudaSuccess || (e = cudaMalloc(&c->a_arena, c->a_bytes)) != cudaSuccess ||
+      (e = cudaMalloc(&c->kv_arena, c->kv_bytes)) != cudaSuccess) {
+    set_error("vcla_create: cudaMalloc failed (%s): weights %.2f GB, activations %.2f GB, kv %.2f GB", cudaGetErrorString(e),
+              c->w_bytes / 1e9, c->a_bytes / 1e9, c->kv_bytes / 1e9);
+    vcla_destroy(c);
+    return -1;
+  }
+  cudaMemset(c->w_arena, 0, c->w_bytes);
+  cudaMemset(c->a_arena, 0, c->a_bytes);
+  layout_weights(c);
+  layout_activations(c);
+  for (int i = 0; i < g.t_layers; ++i) c->tl[i].kv = c->kv_arena + (size_t)i * c->kv_layer_elems;
+  // identity page table (sequence b owns pages [b*pps, (b+1)*pps)); kernels always go through the table
+  std::vector<int32_t> pt((size_t)g.max_batch * c->pages_per_seq);
+  for (size_t i = 0; i < pt.size(); ++i) pt[i] = (int32_t)i;
+  cudaMemcpy(c->page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice);
+  std::vector<int32_t> two(g.max_batch, 2);
+  cudaMemcpy(c->img_row_default, two.data(), two.size() * 4, cudaMemcpyHostToDevice);
+  if (rope_init(g.max_seq + 1, 128, g.rope_theta) || argmax_scratch_init(64)) { vcla_destroy(c); return -1; }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("vcla_create: device error %s", cudaGetErrorString(cudaGetLastError())); vcla_destroy(c); return -1; }
+  *out = c;
+  return 0;
+}
+
+void vcla_destroy(vcla_ctx* c) {
+  if (!c) return;
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  if (c->w_arena) cudaFree(c->w_arena);
+  if (c->a_arena) cudaFree(c->a_arena);
+  if (c->kv_arena) cudaFree(c->kv_arena);
+  if (c->staging) cudaFree(c->staging);
+  delete c;
+}
+
+int vcla_get_config(const vcla_ctx* c, vcla_config* out) { if (!c || !out) return -1; *out = c->cfg; return 0; }
+int vcla_memory_bytes(const vcla_ctx* c, int64_t* w, int64_t* kv, int64_t* a) {
+  if (!c) return -1;
+  if (w) *w = (int64_t)c->w_bytes;
+  if (kv) *kv = (int64_t)c->kv_bytes;
+  if (a) *a = (int64_t)c->a_bytes;
+  return 0;
+}
+int64_t vcla_kernel_launches(vcla_ctx* c, int reset) { int64_t v = c->launches; if (reset) c->launches = 0; return v; }
+
+int vcla_weight_count(const vcla_ctx* c) { return c ? (int)c->slots.size() : 0; }
+int vcla_weight_info(const vcla_ctx* c, int index, const char** name, int64_t shape[4], int* ndim, int* kind) {
+  if (!c || index < 0 || index >= (int)c->slots.size()) { set_error("vcla_weight_info: bad index"); return -1; }
+  const Slot& s = c->slots[index];
+  if (name) *name = s.name.c_str();
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = s.shape[i];
+  if (ndim) *ndim = s.ndim;
+  if (kind) *kind = s.kind;
+  return 0;
+}
+
+static int ensure_staging(vcla_ctx* c, size_t bytes) {
+  if (c->staging_bytes >= bytes) return 0;
+  if (c->staging) cudaFree(c->staging);
+  c->staging = nullptr; c->staging_bytes = 0;
+  VCLA_CUDA_OK(cudaMalloc(&c->staging, bytes));
+  c->staging_bytes = bytes;
+  return 0;
+}
+
+// place a contiguous bf16 [rows, cols] device matrix into a slot's storage
+static int place_matrix(const Slot& s, const bf16* src, cudaStream_t st) {
+  if (s.layout == LAY_INTERLEAVE32) return interleave_rows32(src, (int)s.rows, (int)s.cols, s.which, (bf16*)s.dst, st);
+  if (copy_rows_bf16(src, (int)s.rows, (int)s.cols, (bf16*)s.dst, s.ld, st)) return -1;
+  if (s.dst2) return copy_rows_bf16(src, (int)s.rows, (int)s.cols, (bf16*)s.dst2, (int)s.cols, st);
+  return 0;
+}
+
+int vcla_load_weight(vcla_ctx* c, const char* name, const void* src, int dtype, int on_device, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  auto it = c->slot_index.find(name);
+  if (it == c->slot_index.end()) { set_error("vcla_load_weight: unknown tensor '%s'", name); return -1; }
+  const Slot& s = c->slots[it->second];
+  const size_t n = (size_t)s.rows * s.cols;
+  const size_t esz = dtype == VCLA_F32 ? 4 : 2;
+  if (dtype < 0 || dtype > 2) { set_error("vcla_load_weight: bad dtype"); return -1; }
+  // staging: [raw source copy][bf16 contiguous]
+  const size_t raw_bytes = align_up(n * esz, 256);
+  if (ensure_staging(c, raw_bytes + n * 2 + 256)) return -1;
+  const void* dsrc = src;
+  if (!on_device) {
+    VCLA_CUDA_OK(cudaMemcpyAsync(c->staging, src, n * esz, cudaMemcpyHostToDevice, st));
+    dsrc = c->staging;
+  }
+  if (s.kind == SLOT_VEC) {
+    if (convert_to_f32(dsrc, dtype, (int64_t)n, (float*)s.dst, st)) return -1;
+    if (s.dst2 && convert_to_f32(dsrc, dtype, (int64_t)n, (float*)s.dst2, st)) return -1;
+  } else {
+    bf16* tmp = reinterpret_cast<bf16*>((uint8_t*)c->staging + raw_bytes);
+    if (convert_to_bf16(dsrc, dtype, (int64_t)n, tmp, st)) return -1;
+    if (place_matrix(s, tmp, st)) return -1;
+  }
+  VCLA_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vcla_read_weight(vcla_ctx* c, const char* name, void* dst_host, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  auto it = c->slot_index.find(name);
+  if (it == c->slot_index.end()) { set_error("vcla_read_weight: unknown tensor '%s'", name); return -1; }
+  const Slot& s = c->slots[it->second];
+  if (s.kind == SLOT_VEC) {
+    VCLA_CUDA_OK(cudaMemcpyAsync(dst_host, s.dst, (size_t)s.cols * 4, cudaMemcpyDeviceToHost, st));
+  } else if (s.layout == LAY_INTERLEAVE32) {
+    for (int64_t j0 = 0; j0 < s.rows; j0 += 32) {
+      const int64_t nr = (s.rows - j0) < 32 ? (s.rows - j0) : 32;
+      const bf16* srcp = (const bf16*)s.dst + ((j0 / 32) * 64 + (int64_t)s.which * 32) * s.cols;
+      VCLA_CUDA_OK(cudaMemcpyAsync((bf16*)dst_host + j0 * s.cols, srcp, (size_t)nr * s.cols * 2, cudaMemcpyDeviceToHost, st));
+    }
+  } else {
+    VCLA_CUDA_OK(cudaMemcpy2DAsync(dst_host, (size_t)s.cols * 2, s.dst, (size_t)s.ld * 2, (size_t)s.cols * 2, (size_t)s.rows, cudaMemcpyDeviceToHost, st));
+  }
+  VCLA_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vcla_init_synthetic(vcla_ctx* c, uint32_t seed, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t max_n = 0;
+  for (const Slot& s : c->slots) if (s.kind == SLOT_MAT) max_n = std::max(max_n, (size_t)s.rows * s.cols);
+  if (ensure_staging(c, max_n * 2 + 256)) return -1;
+  const double sigma = 65536.0 / sqrt(3.0);
+  for (const Slot& s : c->slots) {
+    const int64_t n = s.rows * s.cols;
+    const uint32_t sd = fnv1a32(s.name.c_str()) ^ (uint32_t)(seed * 0x9E3779B1u);
+    const float mul = (float)((double)s.std / sigma);
+    if (s.kind == SLOT_VEC) {
+      if (fill_hash_normal(nullptr, (float*)s.dst, n, sd, mul, s.mean, st)) return -1;
+      if (s.dst2 && fill_hash_normal(nullptr, (float*)s.dst2, n, sd, mul, s.mean, st)) return -1;
+    } else {
+      bf16* tmp = (bf16*)c->staging;
+      if (fill_hash_normal(tmp, nullptr, n, sd, mul, s.mean, st)) return -1;
+      if (place_matrix(s, tmp, st)) return -1;
+    }
+  }
+  VCLA_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vcla_reset(vcla_ctx* c, vcla_stream stream) {
+  VCLA_CUDA_OK(cudaMemsetAsync(c->seq_len, 0, (size_t)c->cfg.max_batch * 4, (cudaStream_t)stream));
+  VCLA_CUDA_OK(cudaMemsetAsync(c->attn_counters, 0, (size_t)64 * c->cfg.t_heads * 4, (cudaStream_t)stream));
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// vision encode
+// -------------------------------------------------------------------------------------------------
+static int gemm_bf16(vcla_ctx* c, const bf16* A, int M, int K, int lda, const bf16* W, int N, int ldw, const float* bias, int act, bf16* out, int ldo, cudaStream_t st) {
+  GemmCall g; g.A = A; g.B = W; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldw; g.mode = GEMM_STORE_BF16; g.out = out; g.ldo = ldo; g.bias = bias; g.act = act;
+  count(c); return gemm_tc(g, st);
+}
+static int gemm_f32(vcla_ctx* c, const bf16* A, int M, int K, int lda, const bf16* W, int N, int ldw, const float* bias, int accumulate, float* out, int ldo, cudaStream_t st) {
+  GemmCall g; g.A = A; g.B = W; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldw; g.mode = GEMM_ADD_F32; g.out = out; g.ldo = ldo; g.bias = bias; g.accumulate = accumulate;
+  count(c); return gemm_tc(g, st);
+}
+
+int vcla_vision_encode(vcla_ctx* c, const void* pixels, int pixel_dtype, int B, float* out_dev, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const vcla_config& g = c->cfg;
+  if (B < 1 || B > g.max_batch) { set_error("vision_encode: batch %d exceeds capacity %d", B, g.max_batch); return -1; }
+  const int D = g.v_hidden, NT = c->v_tokens, NP = NT - 1, rows = B * NT;
+  // patch embedding: im2col + GEMM; epilogue adds the position embedding and scatters to token rows 1..NP
+  count(c); if (im2col(pixels, pixel_dtype, B, g.v_image, g.v_patch, c->kpad, c->v_im2col, st)) return -1;
+  {
+    GemmCall gc; gc.A = c->v_im2col; gc.B = c->patch_w; gc.M = B * NP; gc.N = D; gc.K = c->kpad; gc.lda = c->kpad; gc.ldb = c->kpad;
+    gc.mode = GEMM_ADD_F32; gc.out = c->v_hidden; gc.ldo = D; gc.rowtab = c->pos + D; gc.rowtab_period = NP;
+    gc.rows_per_group = NP; gc.group_stride = NT; gc.row_offset = 1;
+    count(c); if (gemm_tc(gc, st)) return -1;
+  }
+  count(c); if (vit_cls_rows(c->v_hidden, B, NT, D, c->cls, c->pos, st)) return -1;
+  count(c); if (layernorm(c->v_hidden, rows, D, c->pre_w, c->pre_b, g.v_eps, nullptr, c->v_hidden, st)) return -1;
+  const float vscale = 1.0f / sqrtf(64.f);
+  for (int i = 0; i < g.v_layers; ++i) {
+    const VisionLayer& L = c->vl[i];
+    count(c); if (layernorm(c->v_hidden, rows, D, L.ln1_w, L.ln1_b, g.v_eps, c->v_norm, nullptr, st)) return -1;
+    if (gemm_bf16(c, c->v_norm, rows, D, D, L.wqkv, 3 * D, D, L.bqkv, ACT_NONE, c->v_qkv, 3 * D, st)) return -1;
+    AttnCall a; a.q = c->v_qkv; a.q_stride = 3 * D; a.k0 = c->v_qkv + D; a.v0 = c->v_qkv + 2 * D; a.kv0_stride = 3 * D; a.n0 = NT;
+    a.out = c->v_attn; a.o_stride = D; a.B = B; a.H = g.v_heads; a.Sq = NT; a.HD = 64; a.scale = vscale; a.causal = 0;
+    count(c); if (attention_prefill(a, st)) return -1;
+    if (gemm_f32(c, c->v_attn, rows, D, D, L.wo, D, D, L.bo, 1, c->v_hidden, D, st)) return -1;
+    count(c); if (layernorm(c->v_hidden, rows, D, L.ln2_w, L.ln2_b, g.v_eps, c->v_norm, nullptr, st)) return -1;
+    if (gemm_bf16(c, c->v_norm, rows, D, D, L.w1, g.v_ffn, D, L.b1, ACT_QUICK_GELU, c->v_ffn, g.v_ffn, st)) return -1;
+    if (gemm_f32(c, c->v_ffn, rows, g.v_ffn, g.v_ffn, L.w2, D, g.v_ffn, L.b2, 1, c->v_hidden, D, st)) return -1;
+  }
+  // post_layernorm on ALL tokens (what the reference does, modeling_visualcla.py:284/350)
+  count(c); if (layernorm(c->v_hidden, rows, D, c->post_w, c->post_b, g.v_eps, c->v_norm, c->v_postln_f32, st)) return -1;
+
+  // ---- Resampler
+  const int R = g.r_hidden, Q = g.r_queries, RL = g.r_layers, qrows = B * Q;
+  count(c); if (broadcast_rows(c->rq, Q, R, B, c->r_hidden, c->r_hidden_bf16, st)) return -1;
+  // K/V of the (layer-invariant) image rows for all layers in one GEMM
+  if (gemm_bf16(c, c->v_norm, rows, R, R, c->r_wkv_all, RL * 2 * R, R, c->r_bkv_all, ACT_NONE, c->r_kvimg, RL * 2 * R, st)) return -1;
+  const float rscale = 1.0f / sqrtf(64.f);
+  for (int i = 0; i < RL; ++i) {
+    const ResamplerLayer& L = c->rl[i];
+    if (gemm_bf16(c, c->r_hidden_bf16, qrows, R, R, L.wqkv, 3 * R, R, L.bqkv, ACT_NONE, c->r_qkv, 3 * R, st)) return -1;
+    AttnCall a; a.q = c->r_qkv; a.q_stride = 3 * R;
+    a.k0 = c->r_qkv + R; a.v0 = c->r_qkv + 2 * R; a.kv0_stride = 3 * R; a.n0 = Q;          // the query rows themselves (:315 cat)
+    a.k1 = c->r_kvimg + (size_t)i * 2 * R; a.v1 = a.k1 + R; a.kv1_stride = RL * 2 * R; a.n1 = NT;   // image rows
+    a.out = c->r_ctx; a.o_stride = R; a.B = B; a.H = g.r_heads; a.Sq = Q; a.HD = 64; a.scale = rscale; a.causal = 0;
+    count(c); if (attention_prefill(a, st)) return -1;
+    if (gemm_f32(c, c->r_ctx, qrows, R, R, L.wo, R, R, L.bo, 1, c->r_hidden, R, st)) return -1;           // dense + residual
+    count(c); if (layernorm(c->r_hidden, qrows, R, L.ln1_w, L.ln1_b, g.r_eps, c->r_hidden_bf16, c->r_hidden, st)) return -1;  // post-LN
+    if (gemm_bf16(c, c->r_hidden_bf16, qrows, R, R, L.wi, g.r_ffn, R, L.bi, ACT_GELU_ERF, c->r_ffn, g.r_ffn, st)) return -1;
+    if (gemm_f32(c, c->r_ffn, qrows, g.r_ffn, g.r_ffn, L.wo2, R, g.r_ffn, L.bo2, 1, c->r_hidden, R, st)) return -1;
+    count(c); if (layernorm(c->r_hidden, qrows, R, L.ln2_w, L.ln2_b, g.r_eps, c->r_hidden_bf16, c->r_hidden, st)) return -1;
+  }
+  // projector -> fp32 image embeddings
+  if (gemm_f32(c, c->r_hidden_bf16, qrows, R, R, c->proj_w, g.t_hidden, R, c->proj_b, 0, c->img_embeds, g.t_hidden, st)) return -1;
+  if (out_dev) VCLA_CUDA_OK(cudaMemcpyAsync(out_dev, c->img_embeds, (size_t)qrows * g.t_hidden * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// prefill
+// -------------------------------------------------------------------------------------------------
+static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X, int B, int splits, float* ws, cudaStream_t st) {
+  GemmCall g; g.A = W; g.B = X; g.M = n_out; g.N = B; g.K = K; g.lda = K; g.ldb = K; g.mode = GEMM_PARTIAL_F32; g.out = ws; g.ldo = n_out;
+  g.splits = splits; g.ws_rows = B; g.weights_are_A = 1;
+  count(c); return gemm_tc(g, st);
+}
+
+static int lm_head_last(vcla_ctx* c, int B, float* logits_dev, int32_t* tok_dev, cudaStream_t st) {
+  // d_resid[B, T] holds the hidden state of the positions to score
+  const vcla_config& g = c->cfg;
+  count(c); if (dec_resid_norm(nullptr, 0, B, c->d_resid, B, g.t_hidden, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
+  if (swap_gemm(c, c->lm_head, g.t_vocab, g.t_hidden, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
+  count(c, 2);
+  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, st);
+}
+
+int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, float* logits_all,
+                 float* last_logits, int32_t* next_tok, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const vcla_config& g = c->cfg;
+  const int nq = g.r_queries, TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
+  const int S = (image_mode == VCLA_IMAGE_AT_HEAD) ? T + nq : T;
+  if (B < 1 || B > g.max_batch || B > 64) { set_error("prefill: batch %d exceeds capacity (max_batch %d, <= 64 per call)", B, g.max_batch); return -1; }
+  if ((long)B * S > g.max_prefill_tokens) { set_error("prefill: %d x %d tokens exceed max_prefill_tokens %d", B, S, g.max_prefill_tokens); return -1; }
+  if (S > g.max_seq) { set_error("prefill: sequence %d exceeds max_seq %d", S, g.max_seq); return -1; }
+  if (image_mode == VCLA_IMAGE_AT_HEAD && T < 2) { set_error("prefill: image_at_head needs >= 2 text tokens"); return -1; }
+  const int rows = B * S;
+  if (vcla_reset(c, stream)) return -1;
+  count(c); if (embed_tokens(ids, B, T, S, TH, c->embed, g.t_vocab, image_mode == VCLA_IMAGE_AT_HEAD ? 1 : 0, nq, c->resid, st)) return -1;
+  if (image_mode != VCLA_TEXT_ONLY) {
+    const int32_t* rs = (image_mode == VCLA_IMAGE_AT_HEAD || img_row == nullptr) ? c->img_row_default : img_row;
+    count(c); if (scatter_image_rows(c->img_embeds, B, nq, TH, rs, S, c->resid, st)) return -1;
+  }
+  const float scale = 1.0f / sqrtf(128.f);
+  for (int i = 0; i < g.t_layers; ++i) {
+    const TextLayer& L = c->tl[i];
+    count(c); if (rmsnorm(c->resid, rows, TH, L.ln1, g.t_eps, c->xn, st)) return -1;
+    if (gemm_bf16(c, c->xn, rows, TH, TH, L.wqkv, 3 * TH, TH, nullptr, ACT_NONE, c->qkv, 3 * TH, st)) return -1;
+    count(c); if (rope_and_cache(c->qkv, B, S, H, 128, g.rope_theta, L.kv, c->page_table, c->pages_per_seq, c->page_tokens, nullptr, st)) return -1;
+    AttnCall a; a.q = c->qkv; a.q_stride = 3 * TH; a.k0 = c->qkv + TH; a.v0 = c->qkv + 2 * TH; a.kv0_stride = 3 * TH; a.n0 = S;
+    a.out = c->attn; a.o_stride = TH; a.B = B; a.H = H; a.Sq = S; a.HD = 128; a.scale = scale; a.causal = 1;
+    count(c); if (attention_prefill(a, st)) return -1;
+    if (gemm_f32(c, c->attn, rows, TH, TH, L.wo, TH, TH, nullptr, 1, c->resid, TH, st)) return -1;
+    count(c); if (rmsnorm(c->resid, rows, TH, L.ln2, g.t_eps, c->xn, st)) return -1;
+    {
+      GemmCall gc; gc.A = c->xn; gc.B = L.wgu; gc.M = rows; gc.N = 2 * F; gc.K = TH; gc.lda = TH; gc.ldb = TH; gc.mode = GEMM_SWIGLU_BF16; gc.out = c->hmid; gc.ldo = F;
+      count(c); if (gemm_tc(gc, st)) return -1;
+    }
+    if (gemm_f32(c, c->hmid, rows, F, F, L.wd, TH, F, nullptr, 1, c->resid, TH, st)) return -1;
+  }
+  if (logits_all) {
+    count(c); if (rmsnorm(c->resid, rows, TH, c->final_norm, g.t_eps, c->xn, st)) return -1;
+    if (gemm_f32(c, c->xn, rows, TH, TH, c->lm_head, g.t_vocab, TH, nullptr, 0, logits_all, g.t_vocab, st)) return -1;
+  }
+  count(c); if (gather_last_rows(c->resid, B, S, TH, c->d_resid, st)) return -1;
+  if (lm_head_last(c, B, last_logits, next_tok, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, S, st)) return -1;
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// decode
+// -------------------------------------------------------------------------------------------------
+static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
+  const vcla_config& g = c->cfg;
+  const int TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
+  count(c); if (embed_tokens_i32(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, st)) return -1;
+  const float scale = 1.0f / sqrtf(128.f);
+  for (int i = 0; i < g.t_layers; ++i) {
+    const TextLayer& L = c->tl[i];
+    // residual += previous layer's down-projection partials ; xn = rmsnorm(residual)
+    count(c); if (dec_resid_norm(i == 0 ? nullptr : c->ws_d, c->sp_d, B, c->d_resid, B, TH, L.ln1, g.t_eps, c->d_xn, st)) return -1;
+    if (swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st)) return -1;
+    DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
+    a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
+    a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.kv_splits = c->kv_splits; a.scale = scale; a.rope_theta = g.rope_theta;
+    count(c); if (attention_decode(a, st)) return -1;
+    if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st)) return -1;
+    count(c); if (dec_resid_norm(c->ws_o, c->sp_o, B, c->d_resid, B, TH, L.ln2, g.t_eps, c->d_xn, st)) return -1;
+    if (swap_gemm(c, L.wgu, 2 * F, TH, c->d_xn, B, c->sp_gu, c->ws_gu, st)) return -1;
+    count(c); if (dec_silu_mul(c->ws_gu, c->sp_gu, B, B, F, c->d_h, st)) return -1;
+    if (swap_gemm(c, L.wd, TH, F, c->d_h, B, c->sp_d, c->ws_d, st)) return -1;
+  }
+  count(c); if (dec_resid_norm(c->ws_d, c->sp_d, B, c->d_resid, B, TH, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
+  if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
+  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, 1, st)) return -1;
+  return 0;
+}
+
+int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, int use_graph, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
+  if (!tok_in || !tok_out) { set_error("decode: null token buffers"); return -1; }
+  if (!use_graph) return decode_enqueue(c, tok_in, B, logits, tok_out, st);
+  GraphKey key{B, tok_in, logits, tok_out};
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    const int64_t before = c->launches;
+    cudaGraph_t graph = nullptr;
+    VCLA_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = decode_enqueue(c, tok_in, B, logits, tok_out, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return -1; }
+    if (e != cudaSuccess) { set_error("decode: graph capture failed: %s", cudaGetErrorString(e)); return -1; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { set_error("decode: graph instantiate failed: %s", cudaGetErrorString(e)); return -1; }
+    c->graph_launches[key] = c->launches - before;
+    c->launches = before;  // capture enqueued nothing
+    c->graphs[key] = exec;
+    it = c->graphs.find(key);
+  }
+  VCLA_CUDA_OK(cudaGraphLaunch(it->second, st));
+  c->launches += c->graph_launches[key];
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// introspection + operator-level entry points
+// -------------------------------------------------------------------------------------------------
+int vcla_read_stage(vcla_ctx* c, const char* stage, int B, float* dst, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const vcla_config& g = c->cfg;
+  const float* src = nullptr; size_t n = 0;
+  if (!strcmp(stage, "vit_out")) { src = c->v_hidden; n = (size_t)B * c->v_tokens * g.v_hidden; }
+  else if (!strcmp(stage, "post_ln")) { src = c->v_postln_f32; n = (size_t)B * c->v_tokens * g.v_hidden; }
+  else if (!strcmp(stage, "resampler_out")) { src = c->r_hidden; n = (size_t)B * g.r_queries * g.r_hidden; }
+  else if (!strcmp(stage, "projector_out")) { src = c->img_embeds; n = (size_t)B * g.r_queries * g.t_hidden; }
+  else { set_error("vcla_read_stage: unknown stage '%s'", stage); return -1; }
+  VCLA_CUDA_OK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, st));
+  VCLA_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int vcla_bench_decode_gemm(vcla_ctx* c, int which, int B, int reps, float* avg_us, int64_t* weight_bytes, vcla_stream stream) {
+  // Times one decode weight-streaming GEMM shape over all layers' (distinct) weights, reps times, with CUDA events on
+  // the launching stream.  13 GB of weights >> 126 MB L2, so every launch streams from HBM.
+  cudaStream_t st = (cudaStream_t)stream;
+  const vcla_config& g = c->cfg;
+  if (B < 1 || B > 64 || which < 0 || which > 4 || reps < 1) { set_error("bench_decode_gemm: bad arguments"); return -1; }
+  const int TH = g.t_hidden, F = g.t_ffn;
+  cudaEvent_t e0, e1;
+  VCLA_CUDA_OK(cudaEventCreate(&e0));
+  VCLA_CUDA_OK(cudaEventCreate(&e1));
+  auto run_all = [&]() -> int {
+    if (which == 4) return swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st);
+    for (int i = 0; i < g.t_layers; ++i) {
+      const TextLayer& L = c->tl[i];
+      int rc = 0;
+      if (which == 0) rc = swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st);
+      if (which == 1) rc = swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st);
+      if (which == 2) rc = swap_gemm(c, L.wgu, 2 * F, TH, c->d_xn, B, c->sp_gu, c->ws_gu, st);
+      if (which == 3) rc = swap_gemm(c, L.wd, TH, F, c->d_h, B, c->sp_d, c->ws_d, st);
+      if (rc) return rc;
+    }
+    return 0;
+  };
+  if (run_all()) return -1;  // warm-up
+  VCLA_CUDA_OK(cudaEventRecord(e0, st));
+  for (int r = 0; r < reps; ++r) if (run_all()) return -1;
+  VCLA_CUDA_OK(cudaEventRecord(e1, st));
+  VCLA_CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  VCLA_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  const int per = which == 4 ? 1 : g.t_layers;
+  if (avg_us) *avg_us = ms * 1000.f / (float)(reps * per);
+  if (weight_bytes) {
+    const int64_t n[5] = {(int64_t)3 * TH * TH, (int64_t)TH * TH, (int64_t)2 * F * TH, (int64_t)TH * F, (int64_t)g.t_vocab * TH};
+    *weight_bytes = n[which] * 2;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int vcla_op_gemm(const void* A, const void* W, int M, int N, int K, int mode, int act, int accumulate, const float* bias, void* out,
+                 int ldo, int splits, int tile_n, int use_reference, vcla_stream stream) {
+  GemmCall g;
+  g.A = (const bf16*)A; g.B = (const bf16*)W; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.mode = mode; g.act = act; g.accumulate = accumulate;
+  g.bias = bias; g.out = out; g.ldo = ldo; g.splits = splits; g.ws_rows = N; g.bn = tile_n; g.weights_are_A = (mode == GEMM_PARTIAL_F32);
+  return use_reference ? gemm_naive(g, (cudaStream_t)stream) : gemm_tc(g, (cudaStream_t)stream);
+}
+int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1, const void* v1,
+                      int kv1_stride, int n1, void* out, int o_stride, int B, int H, int Sq, int HD, float scale, int causal, vcla_stream stream) {
+  AttnCall a; a.q = (const bf16*)q; a.q_stride = q_stride; a.k0 = (const bf16*)k0; a.v0 = (const bf16*)v0; a.kv0_stride = kv0_stride; a.n0 = n0;
+  a.k1 = (const bf16*)k1; a.v1 = (const bf16*)v1; a.kv1_stride = kv1_stride; a.n1 = n1; a.out = (bf16*)out; a.o_stride = o_stride;
+  a.B = B; a.H = H; a.Sq = Sq; a.HD = HD; a.scale = scale; a.causal = causal;
+  return attention_prefill(a, (cudaStream_t)stream);
+}
+int vcla_op_layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps, void* y_bf16, float* y_f32, vcla_stream stream) {
+  return layernorm(x, rows, D, w, b, eps, (bf16*)y_bf16, y_f32, (cudaStream_t)stream);
+}
+int vcla_op_rmsnorm(const float* x, int rows, int D, const float* w, float eps, void* y_bf16, vcla_stream stream) {
+  return rmsnorm(x, rows, D, w, eps, (bf16*)y_bf16, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T, bf16 operands, fp32 accumulation in TMEM.
+//
+// One kernel template serves the whole path:
+//   * prefill / ViT / Resampler / projector: A = activations (tokens are the 128-row UMMA M dimension),
+//     B = nn.Linear weight [N_out, K]; fused epilogues: bias, quick_gelu / erf-gelu, fp32 residual add
+//     with output-row remap (+ position-embedding table), SwiGLU.
+//   * decode ("swap-AB"): A = weight [N_out, K] (streamed once from HBM through TMA), B = the few
+//     activation rows [batch_pad, K]; split-K partials are written to an fp32 workspace that the
+//     next (fused consumer) kernel reduces in a fixed order, so results are deterministic.
+//
+// Structure (per CTA, 192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (+ TMEM
+// alloc/dealloc by the whole warp), warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// smem ring of STAGES x {A 128x64, B BNx64} tiles in the 128B-swizzled K-major layout that both TMA
+// and the UMMA shared-memory descriptors understand; two TMEM accumulator stages so the epilogue of
+// tile i overlaps the MMAs of tile i+1.  Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...
+#include "common.cuh"
+#include "kernels.h"
+
+#include <mutex>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace vcla {
+
+// ------------------------------------------------------------------------------------------------
+// error / device info plumbing shared by all translation units
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+void set_pdl(bool on) { g_pdl = on; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total, total_tiles;
+  int mode, act, accumulate;
+  void* out;
+  int ldo;
+  const float* bias;
+  const float* rowtab;
+  int rowtab_period;
+  int rows_per_group, group_stride, row_offset;
+  int ws_rows;
+  uint64_t policy_a, policy_b;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN, int STAGES>
+struct GemmCfg {
+  static constexpr int A_BYTES = kBlockM * kBlockK * 2;
+  static constexpr int B_BYTES = BN * kBlockK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;  // barriers + tmem slot, + slack for 1024 B alignment
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int CH = BN < 32 ? BN : 32;  // epilogue column chunk
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024 B alignment for SWIZZLE_128B");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_QUICK_GELU) return x / (1.f + __expf(-1.702f * x));
+  if (act == ACT_GELU_ERF) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  return x;
+}
+
+template <int BN, int STAGES, bool SWAP>
+__global__ void __launch_bounds__(kGemmThreads, SWAP ? 2 : 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = GemmCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + C::BAR_OFF;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + C::BAR_OFF + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // everything above overlaps the tail of the previous kernel when launched with PDL
+  pdl_wait();
+  pdl_launch_dependents();
+
+  auto tile_coords = [&](int t, int& m_blk, int& n_blk, int& kb0, int& kb1, int& ks) {
+    m_blk = t % p.m_tiles;
+    int r = t / p.m_tiles;
+    n_blk = r % p.n_tiles;
+    ks = r / p.n_tiles;
+    kb0 = ks * p.kb_per_split;
+    kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, kb0, kb1, ks;
+        tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * kBlockM, full_bar(stage), p.policy_a);
+          tma_load_2d(sa + C::A_BYTES, &tmB, kb * kBlockK, n_blk * BN, full_bar(stage), p.policy_b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t accphase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int m_blk, n_blk, kb0, kb1, ks;
+        tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
+        mbar_wait(tempty_bar(acc), accphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * C::STAGE_BYTES;
+          const uint64_t adesc = make_desc_sw128(sa);
+          const uint64_t bdesc = make_desc_sw128(sa + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                // TMEM lane quadrant this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int m_blk, n_blk, kb0, kb1, ks;
+      tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
+      mbar_wait(tfull_bar(acc), accphase);
+      tc_fence_after();
+      const int row = m_blk * kBlockM + row_in_tile;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+
+      if constexpr (SWAP) {
+        // rows = weight rows (output features), columns = batch.  Coalesced across lanes.
+        float* ws = reinterpret_cast<float*>(p.out);
+#pragma unroll
+        for (int c = 0; c < BN / C::CH; ++c) {
+          uint32_t v[C::CH];
+          if constexpr (C::CH == 32) tmem_ld_32x32(taddr0 + c * C::CH, v);
+          else tmem_ld_32x16(taddr0 + c * C::CH, reinterpret_cast<uint32_t(&)[16]>(v));
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < C::CH; ++i) {
+              const int b = c * C::CH + i;
+              if (b < p.ws_rows) ws[((size_t)ks * p.ws_rows + b) * (size_t)p.ldo + row] = __uint_as_float(v[i]);
+            }
+          }
+        }
+      } else {
+        int orow = row;
+        if (p.rows_per_group > 0) orow = (row / p.rows_per_group) * p.group_stride + (row % p.rows_per_group) + p.row_offset;
+        const int col_tile = n_blk * BN;
+        if (p.mode == GEMM_SWIGLU_BF16) {
+          if constexpr (BN % 64 == 0) {
+            bf16* out = reinterpret_cast<bf16*>(p.out);
+#pragma unroll 1
+            for (int c = 0; c < BN / 64; ++c) {
+              uint32_t g[32], u[32];
+              tmem_ld_32x32(taddr0 + c * 64, g);
+              tmem_ld_32x32(taddr0 + c * 64 + 32, u);
+              tmem_ld_wait();
+              const int col0 = col_tile + c * 64;            // first gate column of this pair (in interleaved space)
+              if (row_ok && col0 < p.N) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  float g0 = __uint_as_float(g[2 * i]), g1 = __uint_as_float(g[2 * i + 1]);
+                  float u0 = __uint_as_float(u[2 * i]), u1 = __uint_as_float(u[2 * i + 1]);
+                  float h0 = g0 / (1.f + __expf(-g0)) * u0;
+                  float h1 = g1 / (1.f + __expf(-g1)) * u1;
+                  pk[i] = pack_bf16x2(h0, h1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)orow * p.ldo + col0 / 2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+              }
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN / C::CH; ++c) {
+            uint32_t v[C::CH];
+            if constexpr (C::CH == 32) tmem_ld_32x32(taddr0 + c * C::CH, v);
+            else tmem_ld_32x16(taddr0 + c * C::CH, reinterpret_cast<uint32_t(&)[16]>(v));
+            tmem_ld_wait();
+            const int col0 = col_tile + c * C::CH;
+            if (!row_ok || col0 >= p.N) continue;
+            const bool full = (col0 + C::CH <= p.N);
+            float x[C::CH];
+#pragma unroll
+            for (int i = 0; i < C::CH; ++i) x[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+              if (full) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                for (int i = 0; i < C::CH / 4; ++i) {
+                  float4 b4 = __ldg(bp + i);
+                  x[4 * i] += b4.x; x[4 * i + 1] += b4.y; x[4 * i + 2] += b4.z; x[4 * i + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < C::CH; ++i) if (col0 + i < p.N) x[i] += __ldg(p.bias + col0 + i);
+              }
+            }
+            if (p.mode == GEMM_STORE_BF16) {
+              if (p.act != ACT_NONE) {
+#pragma unroll
+                for (int i = 0; i < C::CH; ++i) x[i] = apply_act(x[i], p.act);
+              }
+              bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)orow * p.ldo + col0;
+              if (full && (p.ldo & 7) == 0) {
+                uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll
+                for (int i = 0; i < C::CH / 8; ++i)
+                  dst[i] = make_uint4(pack_bf16x2(x[8 * i], x[8 * i + 1]), pack_bf16x2(x[8 * i + 2], x[8 * i + 3]),
+                                      pack_bf16x2(x[8 * i + 4], x[8 * i + 5]), pack_bf16x2(x[8 * i + 6], x[8 * i + 7]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < C::CH; ++i) if (col0 + i < p.N) out[i] = __float2bfloat16(x[i]);
+              }
+            } else {  // GEMM_ADD_F32
+              float* out = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + col0;
+              const float* rt = p.rowtab ? p.rowtab + (size_t)(row % p.rowtab_period) * p.N + col0 : nullptr;
+              if (full && (p.ldo & 3) == 0 && (p.N & 3) == 0) {
+                float4* dst = reinterpret_cast<float4*>(out);
+#pragma unroll
+                for (int i = 0; i < C::CH / 4; ++i) {
+                  float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                  if (rt) {
+                    float4 r4 = __ldg(reinterpret_cast<const float4*>(rt) + i);
+                    o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                  }
+                  if (p.accumulate) {
+                    float4 old = dst[i];
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  dst[i] = o;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < C::CH; ++i) {
+                  if (col0 + i < p.N) {
+                    float o = x[i];
+                    if (rt) o += __ldg(rt + i);
+                    if (p.accumulate) o += out[i];
+                    out[i] = o;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_gemm_once;
+static int g_gemm_init_rc = 0;
+
+template <int BN, int STAGES, bool SWAP>
+static int set_attr() {
+  using C = GemmCfg<BN, STAGES>;
+  VCLA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  return 0;
+}
+
+// tile configurations (BN, STAGES): prefill 256x4 / 128x6 / 64x8 ; decode swap-AB 16x5 / 32x5 / 64x4 (two CTAs per SM)
+static int gemm_init_impl() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  if (set_attr<256, 4, false>()) return -1;
+  if (set_attr<128, 6, false>()) return -1;
+  if (set_attr<64, 8, false>()) return -1;
+  if (set_attr<16, 5, true>()) return -1;
+  if (set_attr<32, 5, true>()) return -1;
+  if (set_attr<64, 4, true>()) return -1;
+  return 0;
+}
+int gemm_init() {
+  std::call_once(g_gemm_once, [] { g_gemm_init_rc = gemm_init_impl(); });
+  return g_gemm_init_rc;
+}
+
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) {
+    set_error("TMA operand must be 16 B aligned with a 16 B-multiple row pitch (ptr %p ld %llu)", ptr, (unsigned long long)ld);
+    return -1;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows %llu cols %llu ld %llu box %u", (int)r, (unsigned long long)rows,
+              (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return -1;
+  }
+  return 0;
+}
+
+template <int BN, int STAGES, bool SWAP>
+static int launch(const GemmCall& c, GemmParams p, cudaStream_t st) {
+  using C = GemmCfg<BN, STAGES>;
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, c.A, c.M, c.K, c.lda, kBlockM)) return -1;
+  if (make_tmap(&tb, c.B, c.N, c.K, c.ldb, BN)) return -1;
+  p.n_tiles = (c.N + BN - 1) / BN;
+  p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int slots = num_sms() * (SWAP ? 2 : 1);
+  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int nattr = 0;
+  if (pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, SWAP>, ta, tb, p));
+  return 0;
+}
+
+int gemm_tc(const GemmCall& c, cudaStream_t st) {
+  if (gemm_init()) return -1;
+  if (c.M <= 0 || c.N <= 0 || c.K <= 0) { set_error("gemm: empty problem"); return -1; }
+  if (c.K % 8 != 0) { set_error("gemm: K (%d) must be a multiple of 8", c.K); return -1; }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = c.M; p.N = c.N; p.K = c.K;
+  p.m_tiles = (c.M + kBlockM - 1) / kBlockM;
+  p.kb_total = (c.K + kBlockK - 1) / kBlockK;
+  p.mode = c.mode; p.act = c.act; p.accumulate = c.accumulate;
+  p.out = c.out; p.ldo = c.ldo; p.bias = c.bias;
+  p.rowtab = c.rowtab; p.rowtab_period = c.rowtab_period > 0 ? c.rowtab_period : 1;
+  p.rows_per_group = c.rows_per_group; p.group_stride = c.group_stride; p.row_offset = c.row_offset;
+  p.ws_rows = c.ws_rows;
+  p.policy_a = c.weights_are_A ? kEvictFirst : kEvictLast;
+  p.policy_b = c.weights_are_A ? kEvictLast : kEvictNormal;
+
+  if (c.mode == GEMM_PARTIAL_F32) {
+    int splits = c.splits > 0 ? c.splits : 1;
+    if (splits > p.kb_total) splits = p.kb_total;
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // every split non-empty
+    if (p.splits != splits) { set_error("gemm: split count %d not realisable for %d k-blocks (use %d)", splits, p.kb_total, p.splits); return -1; }
+    if (c.N > 64 || c.ws_rows < c.N) { set_error("gemm: swap-AB batch rows %d (ws_rows %d) unsupported", c.N, c.ws_rows); return -1; }
+    if (c.N <= 16) return launch<16, 5, true>(c, p, st);
+    if (c.N <= 32) return launch<32, 5, true>(c, p, st);
+    return launch<64, 4, true>(c, p, st);
+  }
+  p.splits = 1;
+  p.kb_per_split = p.kb_total;
+  if (c.mode == GEMM_SWIGLU_BF16 && (c.N % 64) != 0) { set_error("gemm: SwiGLU needs N %% 64 == 0 (N=%d)", c.N); return -1; }
+  int bn = c.bn;
+  if (bn == 0) {
+    // pick the widest tile that still gives every SM work
+    const long tiles256 = (long)p.m_tiles * ((c.N + 255) / 256);
+    const long tiles128 = (long)p.m_tiles * ((c.N + 127) / 128);
+    if (tiles256 >= num_sms() || c.N >= 4096) bn = 256;
+    else if (tiles128 >= num_sms() / 2 || c.N > 64) bn = 128;
+    else bn = 64;
+  }
+  if (bn == 256) return launch<256, 4, false>(c, p, st);
+  if (bn == 128) return launch<128, 6, false>(c, p, st);
+  if (bn == 64) return launch<64, 8, false>(c, p, st);
+  set_error("gemm: unsupported tile N %d", bn);
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// naive reference (tests only): one thread per output element, same epilogue semantics
+// ------------------------------------------------------------------------------------------------
+__global__ void gemm_naive_kernel(const bf16* A, const bf16* B, GemmParams p, int lda, int ldb) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  const int ncols = (p.mode == GEMM_SWIGLU_BF16) ? p.N / 2 : p.N;
+  if (col >= ncols || row >= p.M) return;
+  auto dot = [&](int n, int k0, int k1) {
+    float s = 0.f;
+    for (int k = k0; k < k1; ++k) s += __bfloat162float(A[(size_t)row * lda + k]) * __bfloat162float(B[(size_t)n * ldb + k]);
+    return s;
+  };
+  int orow = row;
+  if (p.rows_per_group > 0) orow = (row / p.rows_per_group) * p.group_stride + (row % p.rows_per_group) + p.row_offset;
+  if (p.mode == GEMM_PARTIAL_F32) {
+    float* ws = reinterpret_cast<float*>(p.out);
+    for (int s = 0; s < p.splits; ++s) {
+      int k0 = s * p.kb_per_split * kBlockK, k1 = min(p.K, (s + 1) * p.kb_per_split * kBlockK);
+      ws[((size_t)s * p.ws_rows + col) * p.ldo + row] = dot(col, k0, k1);
+    }
+    return;
+  }
+  if (p.mode == GEMM_SWIGLU_BF16) {
+    const int gcol = (col / 32) * 64 + (col % 32);
+    float g = dot(gcol, 0, p.K), u = dot(gcol + 32, 0, p.K);
+    reinterpret_cast<bf16*>(p.out)[(size_t)orow * p.ldo + col] = __float2bfloat16(g / (1.f + expf(-g)) * u);
+    return;
+  }
+  float x = dot(col, 0, p.K);
+  if (p.bias) x += p.bias[col];
+  if (p.mode == GEMM_STORE_BF16) {
+    if (p.act == ACT_QUICK_GELU) x = x / (1.f + expf(-1.702f * x));
+    if (p.act == ACT_GELU_ERF) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    reinterpret_cast<bf16*>(p.out)[(size_t)orow * p.ldo + col] = __float2bfloat16(x);
+  } else {
+    float* o = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + col;
+    if (p.rowtab) x += p.rowtab[(size_t)(row % p.rowtab_period) * p.N + col];
+    if (p.accumulate) x += *o;
+    *o = x;
+  }
+}
+
+int gemm_naive(const GemmCall& c, cudaStream_t st) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = c.M; p.N = c.N; p.K = c.K;
+  p.kb_total = (c.K + kBlockK - 1) / kBlockK;
+  p.mode = c.mode; p.act = c.act; p.accumulate = c.accumulate;
+  p.out = c.out; p.ldo = c.ldo; p.bias = c.bias;
+  p.rowtab = c.rowtab; p.rowtab_period = c.rowtab_period > 0 ? c.rowtab_period : 1;
+  p.rows_per_group = c.rows_per_group; p.group_stride = c.group_stride; p.row_offset = c.row_offset;
+  p.ws_rows = c.ws_rows;
+  p.splits = 1; p.kb_per_split = p.kb_total;
+  if (c.mode == GEMM_PARTIAL_F32) {
+    int splits = c.splits > 0 ? c.splits : 1;
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  }
+  const int ncols = (c.mode == GEMM_SWIGLU_BF16) ? c.N / 2 : c.N;
+  dim3 grid((ncols + 127) / 128, c.M);
+  gemm_naive_kernel<<<grid, 128, 0, st>>>(c.A, c.B, p, c.lda, c.ldb);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vcla

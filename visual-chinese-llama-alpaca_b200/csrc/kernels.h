@@ -1,0 +1,144 @@
+// Host-side launch API of every CUDA kernel on the VisualCLA path (internal to libvcla.so).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace vcla {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+int num_sms();
+bool pdl_enabled();
+void set_pdl(bool on);
+
+#define VCLA_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      vcla::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -1;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 GEMM:  D[M,N] = A[M,K] * B[N,K]^T   (both operands K-major bf16, fp32 accumulate in TMEM)
+// ------------------------------------------------------------------------------------------
+enum GemmMode {
+  GEMM_STORE_BF16 = 0,   // out_bf16[orow, col] = act(acc + bias[col])
+  GEMM_ADD_F32 = 1,      // out_f32[orow, col]  = (accumulate ? old : 0) + acc + bias[col] + rowtab[(row % period), col]
+  GEMM_SWIGLU_BF16 = 2,  // B rows interleaved [32 gate | 32 up]: out_bf16[orow, col/2] = silu(g) * u
+  GEMM_PARTIAL_F32 = 3,  // swap-AB split-K partials: ws[(split*ws_rows + col) * ldo + row] = acc   (row = A row)
+};
+enum Act { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
+
+struct GemmCall {
+  const bf16* A = nullptr;   // [M, K], row pitch lda elements
+  const bf16* B = nullptr;   // [N, K], row pitch ldb elements
+  int M = 0, N = 0, K = 0;
+  int lda = 0, ldb = 0;
+  int mode = GEMM_STORE_BF16;
+  void* out = nullptr;
+  int ldo = 0;
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  int accumulate = 0;
+  const float* rowtab = nullptr;
+  int rowtab_period = 1;
+  // output row remap: orow = (row / rows_per_group) * group_stride + (row % rows_per_group) + row_offset
+  int rows_per_group = 0;    // 0 = identity
+  int group_stride = 0;
+  int row_offset = 0;
+  // split-K (GEMM_PARTIAL_F32 only)
+  int splits = 1;
+  int ws_rows = 0;           // padded batch rows in the partial workspace
+  int weights_are_A = 0;     // cache-policy hint: A is the streamed-once operand (decode)
+  int bn = 0;                // tile N override (0 = auto)
+};
+int gemm_tc(const GemmCall& c, cudaStream_t st);
+// correctness reference for the tests only (CUDA-core, one thread per output)
+int gemm_naive(const GemmCall& c, cudaStream_t st);
+int gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
+
+// ------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------
+struct AttnCall {
+  const bf16* q = nullptr; int q_stride = 0;            // q[(b*Sq + i)*q_stride + h*HD + d]
+  const bf16* k0 = nullptr; const bf16* v0 = nullptr; int kv0_stride = 0; int n0 = 0;   // segment 0: n0 rows / batch
+  const bf16* k1 = nullptr; const bf16* v1 = nullptr; int kv1_stride = 0; int n1 = 0;   // segment 1 (optional)
+  bf16* out = nullptr; int o_stride = 0;
+  int B = 0, H = 0, Sq = 0, HD = 0;
+  float scale = 1.f;
+  int causal = 0;
+};
+int attention_prefill(const AttnCall& c, cudaStream_t st);
+
+struct DecodeAttnCall {
+  const float* qkv_partial = nullptr;  // [splits][ws_rows][3*T] fp32 split-K partials of the fused QKV projection
+  int splits = 1, ws_rows = 0;
+  bf16* kv_pages = nullptr;            // this layer: [pages][2][H][page_tokens][HD]
+  const int32_t* page_table = nullptr; // [max_batch][pages_per_seq]
+  int pages_per_seq = 0, page_tokens = 0;
+  const int32_t* seq_len = nullptr;    // [B] tokens already in the cache (the new token is appended at this index)
+  bf16* out = nullptr;                 // [ws_rows][T] attention output (bf16, GEMM operand of o_proj)
+  float* scratch = nullptr;            // [B][H][kv_splits][HD+2]
+  int32_t* counters = nullptr;         // [B][H]
+  int B = 0, H = 0, HD = 0, kv_splits = 1;
+  float scale = 1.f, rope_theta = 10000.f;
+};
+int attention_decode(const DecodeAttnCall& c, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------
+// normalisation / elementwise / data movement
+// ------------------------------------------------------------------------------------------
+// y_bf16 = LN(x) * w + b (fp32 statistics); optionally also writes the fp32 normalised row back (in place ok)
+int layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps, bf16* y_bf16, float* y_f32,
+              cudaStream_t st);
+int rmsnorm(const float* x, int rows, int D, const float* w, float eps, bf16* y_bf16, cudaStream_t st);
+// pixels (B,3,I,I) in f32/f16/bf16 -> im2col rows [B*g*g, Kpad] bf16 (k = c*P*P + ky*P + kx), zero padded
+int im2col(const void* pixels, int dtype, int B, int image, int patch, int kpad, bf16* out, cudaStream_t st);
+// hidden[b, 0, :] = cls + pos[0]
+int vit_cls_rows(float* hidden, int B, int tokens, int D, const float* cls, const float* pos, cudaStream_t st);
+int broadcast_rows(const float* src, int rows, int D, int B, float* dst_f32, bf16* dst_bf16, cudaStream_t st);
+// text embedding gather into the fp32 residual stream: dst[b, dst_pos(t), :] = table[ids[b,t], :]
+//   mode 0: dst_pos = t (text only / placeholder layout: image rows are overwritten afterwards by the projector GEMM)
+//   mode 1: image at head: t<2 -> t ; t>=2 -> t + nq
+int embed_tokens(const int64_t* ids, int B, int T, int S, int D, const bf16* table, int vocab, int mode, int nq,
+                 float* dst, cudaStream_t st);
+int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* dst, cudaStream_t st);
+// copy the projected image rows (B, nq, D) fp32 into the residual stream at per-sample row offsets
+int scatter_image_rows(const float* img, int B, int nq, int D, const int32_t* row_start, int S, float* dst, cudaStream_t st);
+// prefill: RoPE q,k in place in the fused qkv buffer [B*S, 3T] and append k,v to the paged cache
+int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table,
+                   int pages_per_seq, int page_tokens, const int32_t* seq_base, cudaStream_t st);
+int gather_last_rows(const float* hidden, int B, int S, int D, float* dst, cudaStream_t st);
+
+// decode consumers of split-K partials
+// resid[b,:] += sum_s partial[s][b][:]  (partial may be null) ; xn = rmsnorm(resid) -> bf16
+int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, int B, int D, const float* w, float eps,
+                   bf16* xn, cudaStream_t st);
+// h[b, j] = silu(sum_s p[s][b][g(j)]) * (sum_s p[s][b][u(j)])  with the [32 gate | 32 up] interleave
+int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st);
+// logits[b, :] = sum_s partial[s][b][:V] ; tok[b] = argmax (first max wins, like torch.argmax)
+int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits,
+                      int32_t* tok, cudaStream_t st);
+int advance_seq(int32_t* seq_len, int B, int by, cudaStream_t st);
+int rope_init(int max_pos, int head_dim, float theta);
+int argmax_scratch_init(int max_batch);
+const float* rope_cos_table();
+const float* rope_sin_table();
+
+// weights
+int fill_hash_normal(bf16* dst_bf16, float* dst_f32, int64_t n, uint32_t seed, float mul, float offset, cudaStream_t st);
+int convert_to_bf16(const void* src, int dtype, int64_t n, bf16* dst, cudaStream_t st);
+int convert_to_f32(const void* src, int dtype, int64_t n, float* dst, cudaStream_t st);
+// dst rows [r0, r0+rows) of a [*, ld] bf16 matrix <- src [rows, cols] (zero pad cols..ld)
+int copy_rows_bf16(const bf16* src, int rows, int cols, bf16* dst, int ld, cudaStream_t st);
+// interleave gate/up rows in blocks of 32: dst[(j/32)*64 + which*32 + j%32, :] = src[j, :]
+int interleave_rows32(const bf16* src, int rows, int cols, int which, bf16* dst, cudaStream_t st);
+
+}  // namespace vcla

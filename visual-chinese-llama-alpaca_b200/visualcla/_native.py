@@ -1,0 +1,89 @@
+"""ctypes binding of libvcla.so (include/vcla.h).  No CPU fallback: if the library or a CUDA
+device is missing every entry point raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libvcla.so")
+
+VCLA_F32, VCLA_F16, VCLA_BF16 = 0, 1, 2
+TEXT_ONLY, IMAGE_AT_HEAD, IMAGE_PLACEHOLDER = 0, 1, 2
+
+
+class VclaConfig(C.Structure):
+    _fields_ = [
+        ("v_hidden", C.c_int), ("v_layers", C.c_int), ("v_heads", C.c_int), ("v_ffn", C.c_int),
+        ("v_patch", C.c_int), ("v_image", C.c_int), ("v_eps", C.c_float),
+        ("r_hidden", C.c_int), ("r_layers", C.c_int), ("r_heads", C.c_int), ("r_ffn", C.c_int),
+        ("r_queries", C.c_int), ("r_eps", C.c_float),
+        ("t_hidden", C.c_int), ("t_layers", C.c_int), ("t_heads", C.c_int), ("t_ffn", C.c_int),
+        ("t_vocab", C.c_int), ("t_eps", C.c_float), ("rope_theta", C.c_float),
+        ("max_batch", C.c_int), ("max_seq", C.c_int), ("max_prefill_tokens", C.c_int), ("page_tokens", C.c_int),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/vcla.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+_SIGNATURES = [
+    ("vcla_last_error", C.c_char_p, []),
+    ("vcla_version", C.c_char_p, []),
+    ("vcla_create", C.c_int, [C.POINTER(VclaConfig), C.POINTER(_P)]),
+    ("vcla_destroy", None, [_P]),
+    ("vcla_get_config", C.c_int, [_P, C.POINTER(VclaConfig)]),
+    ("vcla_memory_bytes", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("vcla_weight_count", C.c_int, [_P]),
+    ("vcla_weight_info", C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64 * 4), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("vcla_load_weight", C.c_int, [_P, C.c_char_p, _P, C.c_int, C.c_int, _P]),
+    ("vcla_read_weight", C.c_int, [_P, C.c_char_p, _P, _P]),
+    ("vcla_init_synthetic", C.c_int, [_P, C.c_uint32, _P]),
+    ("vcla_reset", C.c_int, [_P, _P]),
+    ("vcla_vision_encode", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    ("vcla_prefill", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    ("vcla_decode_step", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    ("vcla_kernel_launches", C.c_int64, [_P, C.c_int]),
+    ("vcla_read_stage", C.c_int, [_P, C.c_char_p, C.c_int, _P, _P]),
+    ("vcla_op_gemm", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    ("vcla_op_attention", C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+    ("vcla_op_layernorm", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
+    ("vcla_op_rmsnorm", C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, _P, _P]),
+    ("vcla_bench_decode_gemm", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P]),
+    ("vcla_set_pdl", None, [C.c_int]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+
+def load():
+    """Load libvcla.so (once).  Raises NativeError if it was not built -- there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(f"{LIB_PATH} not found: build it with `python visual-chinese-llama-alpaca_b200/build.py` "
+                          "(or __graft_entry__.build()); this package has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in _SIGNATURES:
+        fn = getattr(lib, name)          # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().vcla_last_error()
+        raise NativeError(f"{what}: {msg.decode() if msg else 'unknown error'}")
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())

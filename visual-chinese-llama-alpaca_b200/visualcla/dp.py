@@ -1,0 +1,71 @@
+"""Data-parallel generation over the GPUs of one box.
+
+Every request (image + prompt) is independent through the whole path, so the global batch is split into
+contiguous slices, one per rank; weights are replicated; each rank owns the paged KV cache of its slice.  The only
+exchange is ONE all-gather of the sampled token ids per decode step (NCCL over NVLink/NVSwitch, enqueued on the
+compute stream right after the lm_head+argmax kernels), so every rank -- and the caller on rank 0 -- holds all
+tokens.  With the `gloo` backend (CPU tests) the same code path runs with host tensors.
+"""
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch: int, world: int, rank: int):
+    """Contiguous slice [lo, hi) of the global batch owned by `rank` (first `rem` ranks get one extra)."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_step_tokens(local_tok: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank token vectors of one decode step into the global (B,) vector."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local_tok
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(global_batch, world, r) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    send = local_tok
+    if send.shape[0] != width:      # uneven split: pad to the widest shard so one fixed-size all-gather suffices
+        send = torch.zeros(width, dtype=local_tok.dtype, device=local_tok.device)
+        send[: local_tok.shape[0]] = local_tok
+    recv = torch.empty(world * width, dtype=local_tok.dtype, device=local_tok.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    if all(hi - lo == width for lo, hi in sizes):
+        return recv
+    return torch.cat([recv[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+
+
+@torch.no_grad()
+def generate_dp(model, input_ids: torch.Tensor, pixel_values: Optional[torch.Tensor], max_new_tokens: int, group=None,
+                step_hook: Optional[Callable] = None) -> torch.Tensor:
+    """Greedy DP generation.  `input_ids` (B,T) / `pixel_values` (B,3,I,I) hold the GLOBAL batch on every rank;
+    each rank computes only its slice.  Returns the (B, max_new_tokens) int64 tokens of the whole batch on every rank.
+    `model` is a visualcla.VisualCLAModel (or any object with `._engine` and `._image_layout`)."""
+    from . import _native as N
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = input_ids.shape[0]
+    lo, hi = shard_bounds(B, world, rank)
+    eng = model._engine
+    dev = eng.device
+    ids = input_ids[lo:hi]
+    px = None if pixel_values is None else pixel_values[lo:hi]
+    out = torch.empty(B, max_new_tokens, dtype=torch.int64, device=dev)
+    nloc = hi - lo
+    tok = torch.zeros(max(nloc, 1), dtype=torch.int32, device=dev)
+    if nloc > 0:
+        mode, rows = model._image_layout(ids, px)
+        if mode != N.TEXT_ONLY:
+            eng.vision_encode(px)
+        _, first, _ = eng.prefill(ids, mode, rows, all_logits=False, last_logits=False)
+        tok[:nloc].copy_(first)
+    for step in range(max_new_tokens):
+        if step > 0 and nloc > 0:
+            eng.decode_step(tok[:nloc], tok[:nloc], None)
+        out[:, step] = gather_step_tokens(tok[:nloc], B, group)
+        if step_hook is not None:
+            step_hook(step)
+    return out

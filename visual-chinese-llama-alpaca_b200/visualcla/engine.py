@@ -1,0 +1,175 @@
+"""Thin Python owner of a native `vcla_ctx` (include/vcla.h): creation from a path config, weight loading by
+reference state-dict names, and the three phases of the path.  All tensors are torch CUDA tensors used as raw
+device buffers; every kernel is enqueued on torch's current stream."""
+import ctypes as C
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+_DTYPE = {torch.float32: N.VCLA_F32, torch.float16: N.VCLA_F16, torch.bfloat16: N.VCLA_BF16}
+
+PATH_KEYS = ["v_hidden", "v_layers", "v_heads", "v_ffn", "v_patch", "v_image", "v_eps",
+             "r_hidden", "r_layers", "r_heads", "r_ffn", "r_queries", "r_eps",
+             "t_hidden", "t_layers", "t_heads", "t_ffn", "t_vocab", "t_eps", "rope_theta"]
+
+
+def path_config_7b() -> Dict:
+    """VisualCLA-7B-v0.1 shapes (SURVEY.md section 8 constants)."""
+    return dict(v_hidden=1024, v_layers=24, v_heads=16, v_ffn=4096, v_patch=14, v_image=224, v_eps=1e-5,
+                r_hidden=1024, r_layers=6, r_heads=16, r_ffn=4096, r_queries=64, r_eps=1e-12,
+                t_hidden=4096, t_layers=32, t_heads=32, t_ffn=11008, t_vocab=49958, t_eps=1e-6, rope_theta=10000.0)
+
+
+class Engine:
+    def __init__(self, path_cfg: Dict, max_batch: int = 8, max_seq: int = 512, max_prefill_tokens: Optional[int] = None,
+                 device: Optional[torch.device] = None, page_tokens: int = 64):
+        if not torch.cuda.is_available():
+            raise N.NativeError("visualcla (B200) needs a CUDA device: there is no CPU fallback")
+        self.lib = N.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.path_cfg = {k: path_cfg[k] for k in PATH_KEYS}
+        self.max_batch, self.max_seq = int(max_batch), int(max_seq)
+        self.max_prefill_tokens = int(max_prefill_tokens or max_batch * max_seq)
+        cfg = N.VclaConfig(**self.path_cfg, max_batch=self.max_batch, max_seq=self.max_seq,
+                           max_prefill_tokens=self.max_prefill_tokens, page_tokens=page_tokens)
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_create(C.byref(cfg), C.byref(self._ctx)), "vcla_create")
+        self.nq = self.path_cfg["r_queries"]
+        self.vocab = self.path_cfg["t_vocab"]
+        self._names = None
+
+    # ---- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.vcla_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def memory_bytes(self) -> Tuple[int, int, int]:
+        w, k, a = C.c_int64(), C.c_int64(), C.c_int64()
+        N.check(self.lib.vcla_memory_bytes(self._ctx, C.byref(w), C.byref(k), C.byref(a)), "vcla_memory_bytes")
+        return w.value, k.value, a.value
+
+    # ---- weights ----------------------------------------------------------------------------
+    def weight_table(self):
+        """[(name, shape, kind)] in the reference's state-dict naming; kind 0 = bf16 matrix, 1 = f32 vector."""
+        if self._names is None:
+            out = []
+            for i in range(self.lib.vcla_weight_count(self._ctx)):
+                name, shape, nd, kind = C.c_char_p(), (C.c_int64 * 4)(), C.c_int(), C.c_int()
+                N.check(self.lib.vcla_weight_info(self._ctx, i, C.byref(name), C.byref(shape), C.byref(nd), C.byref(kind)), "vcla_weight_info")
+                out.append((name.value.decode(), tuple(shape[j] for j in range(nd.value)), kind.value))
+            self._names = out
+        return self._names
+
+    def load_weight(self, name: str, tensor: torch.Tensor):
+        t = tensor.detach()
+        if t.dtype not in _DTYPE:
+            t = t.float()
+        t = t.contiguous()
+        on_dev = 1 if t.is_cuda else 0
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_load_weight(self._ctx, name.encode(), N.ptr(t), _DTYPE[t.dtype], on_dev, self._stream()),
+                    f"vcla_load_weight({name})")
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True, prefix: str = ""):
+        table = {n: (s, k) for n, s, k in self.weight_table()}
+        loaded, unexpected = set(), []
+        for k, v in sd.items():
+            name = prefix + k
+            if name not in table:
+                unexpected.append(name)
+                continue
+            if tuple(v.shape) != tuple(table[name][0]):
+                raise ValueError(f"shape mismatch for {name}: checkpoint {tuple(v.shape)} vs model {tuple(table[name][0])}")
+            self.load_weight(name, v)
+            loaded.add(name)
+        return loaded, unexpected
+
+    def read_weight(self, name: str) -> torch.Tensor:
+        table = {n: (s, k) for n, s, k in self.weight_table()}
+        shape, kind = table[name]
+        out = torch.empty(shape, dtype=torch.bfloat16 if kind == 0 else torch.float32)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_read_weight(self._ctx, name.encode(), N.ptr(out), self._stream()), f"vcla_read_weight({name})")
+        return out
+
+    def init_synthetic(self, seed: int = 0):
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_init_synthetic(self._ctx, seed, self._stream()), "vcla_init_synthetic")
+
+    # ---- the path ---------------------------------------------------------------------------
+    def vision_encode(self, pixel_values: torch.Tensor, return_embeds: bool = False) -> Optional[torch.Tensor]:
+        px = pixel_values
+        if px.device != self.device:
+            px = px.to(self.device, non_blocking=True)
+        if px.dtype not in _DTYPE:
+            px = px.float()
+        px = px.contiguous()
+        B = px.shape[0]
+        I = self.path_cfg["v_image"]
+        if tuple(px.shape[1:]) != (3, I, I):
+            raise ValueError(f"Input image size ({px.shape[2]}*{px.shape[3]}) doesn't match model ({I}*{I}).")
+        out = torch.empty(B, self.nq, self.path_cfg["t_hidden"], dtype=torch.float32, device=self.device) if return_embeds else None
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_vision_encode(self._ctx, N.ptr(px), _DTYPE[px.dtype], B, N.ptr(out), self._stream()), "vcla_vision_encode")
+        return out
+
+    def prefill(self, input_ids: torch.Tensor, image_mode: int, img_rows: Optional[torch.Tensor] = None,
+                all_logits: bool = False, last_logits: bool = True):
+        ids = input_ids.to(self.device, dtype=torch.int64).contiguous()
+        B, T = ids.shape
+        S = T + self.nq if image_mode == N.IMAGE_AT_HEAD else T
+        la = torch.empty(B, S, self.vocab, dtype=torch.float32, device=self.device) if all_logits else None
+        ll = torch.empty(B, self.vocab, dtype=torch.float32, device=self.device) if last_logits else None
+        tok = torch.empty(B, dtype=torch.int32, device=self.device)
+        rows = None if img_rows is None else img_rows.to(self.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_prefill(self._ctx, N.ptr(ids), B, T, image_mode, N.ptr(rows), N.ptr(la), N.ptr(ll), N.ptr(tok),
+                                          self._stream()), "vcla_prefill")
+        return ll, tok, la
+
+    def decode_step(self, tok_in: torch.Tensor, tok_out: torch.Tensor, logits: Optional[torch.Tensor] = None, use_graph: bool = True):
+        """tok_in / tok_out: int32 CUDA tensors of shape (B,) that stay alive (and at the same address) across steps."""
+        B = tok_in.shape[0]
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_decode_step(self._ctx, N.ptr(tok_in), B, N.ptr(logits), N.ptr(tok_out), 1 if use_graph else 0,
+                                              self._stream()), "vcla_decode_step")
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_reset(self._ctx, self._stream()), "vcla_reset")
+
+    def kernel_launches(self, reset: bool = False) -> int:
+        return int(self.lib.vcla_kernel_launches(self._ctx, 1 if reset else 0))
+
+    def bench_decode_gemm(self, which: int, B: int, reps: int = 3):
+        """(mean microseconds per launch, weight bytes per launch) of one decode GEMM shape; see vcla.h."""
+        us, nbytes = C.c_float(), C.c_int64()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_bench_decode_gemm(self._ctx, which, B, reps, C.byref(us), C.byref(nbytes), self._stream()), "vcla_bench_decode_gemm")
+        return us.value, nbytes.value
+
+    def read_stage(self, stage: str, B: int) -> torch.Tensor:
+        c = self.path_cfg
+        shapes = {"vit_out": (B, (c["v_image"] // c["v_patch"]) ** 2 + 1, c["v_hidden"]),
+                  "post_ln": (B, (c["v_image"] // c["v_patch"]) ** 2 + 1, c["v_hidden"]),
+                  "resampler_out": (B, c["r_queries"], c["r_hidden"]),
+                  "projector_out": (B, c["r_queries"], c["t_hidden"])}
+        out = torch.empty(shapes[stage], dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_read_stage(self._ctx, stage.encode(), B, N.ptr(out), self._stream()), f"vcla_read_stage({stage})")
+        return out
