@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the VisualCLA hot path on B200 (contract: see the task's section (4) and DESIGN.md "Measurement").
+
+A "step" = one pass of the whole path over one batch of synthetic requests:
+    B images (224x224) + 64-token prompts -> ViT-L/14 -> Resampler -> projector -> LLaMA-7B prefill (S = 128)
+    -> 256 greedy tokens (KV-cached decode, CUDA graph), i.e. BASELINE.json configs[1] (batch 8 per GPU).
+metric = images+256-token generations per second (whole job, all GPUs).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3            # this repo's CUDA path
+  python bench.py --impl reference ...                      # reference algorithm on the host cores (CPU oracle port)
+  torchrun --nproc-per-node N bench.py --gpus N ...         # data parallel, one rank per GPU, weak scaling
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "visual-chinese-llama-alpaca_b200"))
+
+METRIC = "image+64-token-prompt -> 256-token generations per second (VisualCLA-7B path)"
+UNIT = "gens/s"
+T_TEXT, N_NEW, NQ = 64, 256, 64
+S_PREFILL = T_TEXT + NQ
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=8)
+    ap.add_argument("--new-tokens", type=int, default=N_NEW)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("VCLA_PDL", "1")))
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# algorithmic work (SURVEY.md section 8d / BASELINE.md section 3)
+# ----------------------------------------------------------------------------------------------------------------
+BODY_PARAMS, LM_PARAMS = 6.476e9, 0.2046e9
+VISION_FLOP_PER_IMAGE = 179.2e9
+KV_BYTES_PER_TOKEN = 524288
+
+
+def decode_step_bytes(B, ctx):
+    return (BODY_PARAMS + LM_PARAMS) * 2 + B * (ctx + 1) * KV_BYTES_PER_TOKEN
+
+
+def prefill_flops(B, S):
+    per_tok = 2 * BODY_PARAMS + 4 * 4096 * 32 * (S + 1) / 2
+    return B * (VISION_FLOP_PER_IMAGE + S * per_tok + 2 * LM_PARAMS)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(B, seed=1234):
+    """randn pixels (CLIP-normalised scale), ids = [BOS, <img>, </img>, uniform random...]."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    px = torch.randn(B, 3, 224, 224, generator=g).half()
+    ids = torch.randint(3, 49954, (B, T_TEXT), generator=g)
+    ids[:, 0], ids[:, 1], ids[:, 2] = 1, 49954, 49955
+    return px, ids
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference algorithm on the host cores, bounded sample, extrapolated
+# ----------------------------------------------------------------------------------------------------------------
+_CPU_STATE = {}
+
+
+def cpu_reference_sample(B, n_new, sample_B=2, decode_steps=2, threads=None):
+    """One bounded CPU sample of the workload with the oracle port (weights are built once per process)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import visualcla_oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = O.PathConfig()
+    if "w" not in _CPU_STATE:
+        block = torch.randn(1 << 20)
+        w = {}
+        for name, shape, std, mean in O.weight_specs(cfg):      # values are irrelevant for timing; finite + non-denormal
+            n = 1
+            for s in shape:
+                n *= s
+            reps = (n + block.numel() - 1) // block.numel()
+            w[name] = (block.repeat(reps)[:n] * float(std) + float(mean)).reshape(shape)
+        _CPU_STATE["w"] = w
+    w = _CPU_STATE["w"]
+    px, ids = O.make_inputs(cfg, B, T_TEXT, seed=1234)
+    sample_B = min(sample_B, B)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        img = O.vision_encode(w, cfg, px[:sample_B])
+        t_vis = (time.perf_counter() - t0) * (B / sample_B)
+        s0, s1, _, s3 = O.special_ids(cfg)
+        x = O.splice(w, cfg, ids[:sample_B], img, True, s0, s1, s3)
+        cache = O.KVCache(cfg.t_layers)
+        t0 = time.perf_counter()
+        O.llama_forward(w, cfg, x, cache, last_only=True)
+        t_pre = (time.perf_counter() - t0) * (B / sample_B)
+        # decode at the full batch B (CPU decode is weight-bandwidth bound: time per step ~ independent of B)
+        reps = (B + sample_B - 1) // sample_B
+        for i in range(cfg.t_layers):
+            cache.k[i] = cache.k[i].repeat(reps, 1, 1, 1)[:B]
+            cache.v[i] = cache.v[i].repeat(reps, 1, 1, 1)[:B]
+        tok = torch.randint(3, 49954, (B,))
+        t0 = time.perf_counter()
+        for _ in range(decode_steps):
+            e = w["text_model.model.embed_tokens.weight"][tok].unsqueeze(1)
+            tok = O.llama_forward(w, cfg, e, cache, last_only=True)[:, -1].argmax(-1)
+        t_dec = (time.perf_counter() - t0) / decode_steps
+    total = t_vis + t_pre + (n_new - 1) * t_dec
+    return {"value": B / total, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle/visualcla_oracle.py fp32 on {threads} host threads: vision+prefill measured on {sample_B} of {B} requests "
+                      f"(x{B / sample_B:g}), {decode_steps} decode steps at batch {B}; extrapolated to {n_new} tokens "
+                      f"(vision {t_vis:.2f}s + prefill {t_pre:.2f}s + {n_new - 1} x {t_dec:.3f}s)",
+            "seconds_per_step_extrapolated": total}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.batch_per_gpu * args.gpus
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_sample(B, args.new_tokens)
+        if i >= args.warmup:
+            vals.append(r)
+    value = statistics.mean(v["value"] for v in vals)
+    last = vals[-1]
+    last["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * B / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"configs[1]: batch {args.batch_per_gpu}/GPU x {args.gpus} GPU, 224x224 images, "
+                                            f"{T_TEXT}-token prompts, {args.new_tokens}-token greedy decode (host CPU, no GPU)"},
+            "cpu_baseline": last, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import visualcla
+    from visualcla import _native
+    from visualcla.dp import generate_dp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: this repo has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    _native.load().vcla_set_pdl(1 if args.pdl else 0)
+    Bl, B, n_new = args.batch_per_gpu, args.batch_per_gpu * world, args.new_tokens
+    max_seq = S_PREFILL + n_new + 1
+    model = visualcla.VisualCLAModel.from_synthetic("7b", seed=0, max_batch=Bl, max_seq=max_seq, max_prefill_tokens=Bl * S_PREFILL)
+    model.image_at_head = True
+    eng = model._engine
+    px_h, ids_h = synth_inputs(B)
+    px_h, ids_h = px_h.pin_memory(), ids_h.pin_memory()
+    px_d, ids_d = px_h.cuda(non_blocking=True), ids_h.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    ev = {}
+
+    def phase_hook(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev.setdefault(name, []).append(e)
+
+    def step_device():
+        return generate_dp(model, ids_d, px_d, n_new, phase_hook=phase_hook)
+
+    def step_e2e():
+        out = generate_dp(model, ids_h, px_h, n_new)   # pinned host inputs: each rank copies its slice host -> device inside the timed region
+        return out.cpu()                              # device -> host read of the result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(k):
+            out = fn()
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), out
+
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    ev.clear()
+    eng.kernel_launches(reset=True)
+    with ClockSampler(local) as clocks:
+        ms, out = timed(step_device, args.steps)
+    launches = eng.kernel_launches(reset=True)
+    value = B * args.steps / (ms / 1000.0)
+    # phase split on this rank (events recorded on the compute stream)
+    pre_ms = [a.elapsed_time(b) for a, b in zip(ev.get("start", []), ev.get("prefill_done", []))]
+    dec_ms = [a.elapsed_time(b) for a, b in zip(ev.get("prefill_done", []), ev.get("done", []))]
+    step_e2e()
+    ms_e2e, out_e2e = timed(step_e2e, args.steps)
+    e2e_value = B * args.steps / (ms_e2e / 1000.0)
+    assert torch.equal(out_e2e, out.cpu()), "e2e and device-resident runs must produce the same tokens"
+
+    pk = peaks()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (randn 224x224 pixels, uniform random token ids, hash-normal weights of the VisualCLA-7B architecture)",
+            "config": {"workload": f"configs[1]: batch {Bl} per GPU x {world} GPU, 224x224 images, {T_TEXT}-token prompts (S={S_PREFILL} with 64 image tokens), "
+                                   f"{n_new}-token greedy decode, EOS disabled", "global_batch": B, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2: every decode step streams 13.4 GB of weights (>> 126 MB L2)", "pdl": bool(args.pdl)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(px_h.numel() * 2 + ids_h.numel() * 8),
+                    "d2h_bytes_per_step": int(B * n_new * 8), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks.summary()}
+    if pre_ms and dec_ms:
+        pre, dec = statistics.mean(pre_ms), statistics.mean(dec_ms)
+        ctx_mean = S_PREFILL + (n_new - 1) / 2.0
+        dec_bytes = sum(decode_step_bytes(Bl, S_PREFILL + i) for i in range(n_new - 1))
+        line["phases"] = {
+            "prefill_ms": pre, "decode_ms": dec, "decode_ms_per_token": dec / max(1, n_new - 1),
+            "prefill": {"bound": "tensor", "achieved": prefill_flops(Bl, S_PREFILL) / (pre / 1e3) / 1e12, "peak": pk["tf_sus"], "unit": "TFLOP/s",
+                        "frac": prefill_flops(Bl, S_PREFILL) / (pre / 1e3) / 1e12 / pk["tf_sus"], "note": "vision + LLaMA prefill, algorithmic FLOPs / CUDA-event time, of " + pk["source"] + " sustained bf16 peak"},
+            "decode": {"bound": "hbm", "achieved": dec_bytes / (dec / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                       "frac": dec_bytes / (dec / 1e3) / 1e9 / pk["hbm"], "note": f"{n_new - 1} graph-captured decode steps, algorithmic bytes (13.361 GB weights + KV, mean ctx {ctx_mean:.0f}) / CUDA-event time"}}
+    # dominant kernel: the swap-AB tcgen05 weight-streaming GEMM (gate/up shape has the largest share), timed live
+    if rank == 0:
+        shapes = ["qkv", "o_proj", "gate_up", "down_proj", "lm_head"]
+        per = {}
+        tot_us = 0.0
+        for i, nm in enumerate(shapes):
+            us, nbytes = eng.bench_decode_gemm(i, Bl, reps=3)
+            mult = 1 if nm == "lm_head" else 32
+            per[nm] = {"us": us, "GBps": nbytes / us / 1e3, "bytes": nbytes}
+            tot_us += us * mult
+        dom = per["gate_up"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("gate_up_dram_bytes_per_launch")
+        line["roofline"] = {"bound": "hbm", "achieved": dom["GBps"], "peak": pk["hbm"], "unit": "GB/s", "frac": dom["GBps"] / pk["hbm"], "traffic": traffic,
+                            "kernel": "gemm_tc_kernel<BN,5,swap-AB> fused gate/up projection (22016x4096 bf16 weights, 180.4 MB algorithmic bytes per launch)",
+                            "of": pk["source"] + " copy bandwidth (burst, kernel timed alone over 32 layers' distinct weights)",
+                            "per_shape": per, "gemm_us_per_decode_step": tot_us}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_reference_sample(Bl, n_new)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,8 @@ LOGIT_TOL = 4e-2      # relative to max |logit|
 
 
 def _rel_err(a, b):
-    a, b = torch.as_tensor(np.asarray(a)).float().cpu(), torch.as_tensor(np.asarray(b)).float().cpu()
+    a = a.detach().float().cpu() if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a)).float()
+    b = b.detach().float().cpu() if isinstance(b, torch.Tensor) else torch.as_tensor(np.asarray(b)).float()
     assert a.shape == b.shape, (a.shape, b.shape)
     return (a - b).abs().max().item() / max(1e-6, b.abs().max().item())
 

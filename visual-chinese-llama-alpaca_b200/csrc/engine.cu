@@ -34,7 +34,7 @@ struct Slot {
   void* dst = nullptr;     // storage (bf16 for MAT, f32 for VEC) at the slot's first row
   int ld = 0;              // storage row pitch (elements) for MAT
   void* dst2 = nullptr;    // optional second copy (resampler k/v also live in the all-layer KV weight)
-  float std = 0.f, mean = 0.f;
+  double std = 0.0; float mean = 0.f;
 };
 
 struct VisionLayer {
@@ -112,6 +112,7 @@ struct vcla_ctx {
   std::map<GraphKey, int64_t> graph_launches;
   int64_t launches = 0;
   void* staging = nullptr; size_t staging_bytes = 0;
+  cudaStream_t cap_stream = nullptr;   // graph capture is illegal on the legacy default stream torch uses
 };
 
 namespace {
@@ -133,7 +134,7 @@ T* a_alloc(vcla_ctx* c, size_t n) {
   return p;
 }
 
-void add_slot(vcla_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, int kind, void* dst, int ld, float std_,
+void add_slot(vcla_ctx* c, const std::string& name, std::initializer_list<int64_t> shape, int kind, void* dst, int ld, double std_,
               float mean_, int layout = LAY_PLAIN, int which = 0, void* dst2 = nullptr) {
   if (c->w_arena == nullptr) return;  // sizing pass: no registry
   Slot s;
@@ -156,41 +157,41 @@ void layout_weights(vcla_ctx* c) {
   const int D = g.v_hidden, Fv = g.v_ffn;
   const std::string vp = "vision_model.vision_model.";
   c->cls = w_alloc<float>(c, D);
-  add_slot(c, vp + "embeddings.class_embedding", {D}, SLOT_VEC, c->cls, 0, 1.0f, 0.f);
+  add_slot(c, vp + "embeddings.class_embedding", {D}, SLOT_VEC, c->cls, 0, 1.0, 0.f);
   c->patch_w = w_alloc<bf16>(c, (size_t)D * c->kpad);
-  add_slot(c, vp + "embeddings.patch_embedding.weight", {D, 3, g.v_patch, g.v_patch}, SLOT_MAT, c->patch_w, c->kpad, 1.0f / sqrtf((float)c->kpatch), 0.f);
+  add_slot(c, vp + "embeddings.patch_embedding.weight", {D, 3, g.v_patch, g.v_patch}, SLOT_MAT, c->patch_w, c->kpad, 1.0 / sqrt((double)c->kpatch), 0.f);
   c->pos = w_alloc<float>(c, (size_t)c->v_tokens * D);
-  add_slot(c, vp + "embeddings.position_embedding.weight", {c->v_tokens, D}, SLOT_VEC, c->pos, 0, 0.5f, 0.f);
-  c->pre_w = w_alloc<float>(c, D); add_slot(c, vp + "pre_layrnorm.weight", {D}, SLOT_VEC, c->pre_w, 0, 0.1f, 1.f);
-  c->pre_b = w_alloc<float>(c, D); add_slot(c, vp + "pre_layrnorm.bias", {D}, SLOT_VEC, c->pre_b, 0, 0.1f, 0.f);
+  add_slot(c, vp + "embeddings.position_embedding.weight", {c->v_tokens, D}, SLOT_VEC, c->pos, 0, 0.5, 0.f);
+  c->pre_w = w_alloc<float>(c, D); add_slot(c, vp + "pre_layrnorm.weight", {D}, SLOT_VEC, c->pre_w, 0, 0.1, 1.f);
+  c->pre_b = w_alloc<float>(c, D); add_slot(c, vp + "pre_layrnorm.bias", {D}, SLOT_VEC, c->pre_b, 0, 0.1, 0.f);
   c->vl.resize(g.v_layers);
   for (int i = 0; i < g.v_layers; ++i) {
     VisionLayer& L = c->vl[i];
     const std::string lp = vp + "encoder.layers." + std::to_string(i) + ".";
-    L.ln1_w = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm1.weight", {D}, SLOT_VEC, L.ln1_w, 0, 0.1f, 1.f);
-    L.ln1_b = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm1.bias", {D}, SLOT_VEC, L.ln1_b, 0, 0.1f, 0.f);
-    L.ln2_w = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm2.weight", {D}, SLOT_VEC, L.ln2_w, 0, 0.1f, 1.f);
-    L.ln2_b = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm2.bias", {D}, SLOT_VEC, L.ln2_b, 0, 0.1f, 0.f);
+    L.ln1_w = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm1.weight", {D}, SLOT_VEC, L.ln1_w, 0, 0.1, 1.f);
+    L.ln1_b = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm1.bias", {D}, SLOT_VEC, L.ln1_b, 0, 0.1, 0.f);
+    L.ln2_w = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm2.weight", {D}, SLOT_VEC, L.ln2_w, 0, 0.1, 1.f);
+    L.ln2_b = w_alloc<float>(c, D); add_slot(c, lp + "layer_norm2.bias", {D}, SLOT_VEC, L.ln2_b, 0, 0.1, 0.f);
     L.wqkv = w_alloc<bf16>(c, (size_t)3 * D * D);
     L.bqkv = w_alloc<float>(c, 3 * D);
     const char* pr[3] = {"q_proj", "k_proj", "v_proj"};
     for (int j = 0; j < 3; ++j) {
-      add_slot(c, lp + "self_attn." + pr[j] + ".weight", {D, D}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)j * D * D : nullptr, D, 1.5f / sqrtf((float)D), 0.f);
-      add_slot(c, lp + "self_attn." + pr[j] + ".bias", {D}, SLOT_VEC, L.bqkv ? L.bqkv + j * D : nullptr, 0, 0.1f, 0.f);
+      add_slot(c, lp + "self_attn." + pr[j] + ".weight", {D, D}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)j * D * D : nullptr, D, 1.5 / sqrt((double)D), 0.f);
+      add_slot(c, lp + "self_attn." + pr[j] + ".bias", {D}, SLOT_VEC, L.bqkv ? L.bqkv + j * D : nullptr, 0, 0.1, 0.f);
     }
-    L.wo = w_alloc<bf16>(c, (size_t)D * D); add_slot(c, lp + "self_attn.out_proj.weight", {D, D}, SLOT_MAT, L.wo, D, 0.5f / sqrtf((float)D), 0.f);
-    L.bo = w_alloc<float>(c, D); add_slot(c, lp + "self_attn.out_proj.bias", {D}, SLOT_VEC, L.bo, 0, 0.05f, 0.f);
-    L.w1 = w_alloc<bf16>(c, (size_t)Fv * D); add_slot(c, lp + "mlp.fc1.weight", {Fv, D}, SLOT_MAT, L.w1, D, 1.0f / sqrtf((float)D), 0.f);
-    L.b1 = w_alloc<float>(c, Fv); add_slot(c, lp + "mlp.fc1.bias", {Fv}, SLOT_VEC, L.b1, 0, 0.1f, 0.f);
-    L.w2 = w_alloc<bf16>(c, (size_t)D * Fv); add_slot(c, lp + "mlp.fc2.weight", {D, Fv}, SLOT_MAT, L.w2, Fv, 0.5f / sqrtf((float)Fv), 0.f);
-    L.b2 = w_alloc<float>(c, D); add_slot(c, lp + "mlp.fc2.bias", {D}, SLOT_VEC, L.b2, 0, 0.05f, 0.f);
+    L.wo = w_alloc<bf16>(c, (size_t)D * D); add_slot(c, lp + "self_attn.out_proj.weight", {D, D}, SLOT_MAT, L.wo, D, 0.5 / sqrt((double)D), 0.f);
+    L.bo = w_alloc<float>(c, D); add_slot(c, lp + "self_attn.out_proj.bias", {D}, SLOT_VEC, L.bo, 0, 0.05, 0.f);
+    L.w1 = w_alloc<bf16>(c, (size_t)Fv * D); add_slot(c, lp + "mlp.fc1.weight", {Fv, D}, SLOT_MAT, L.w1, D, 1.0 / sqrt((double)D), 0.f);
+    L.b1 = w_alloc<float>(c, Fv); add_slot(c, lp + "mlp.fc1.bias", {Fv}, SLOT_VEC, L.b1, 0, 0.1, 0.f);
+    L.w2 = w_alloc<bf16>(c, (size_t)D * Fv); add_slot(c, lp + "mlp.fc2.weight", {D, Fv}, SLOT_MAT, L.w2, Fv, 0.5 / sqrt((double)Fv), 0.f);
+    L.b2 = w_alloc<float>(c, D); add_slot(c, lp + "mlp.fc2.bias", {D}, SLOT_VEC, L.b2, 0, 0.05, 0.f);
   }
-  c->post_w = w_alloc<float>(c, D); add_slot(c, vp + "post_layernorm.weight", {D}, SLOT_VEC, c->post_w, 0, 0.1f, 1.f);
-  c->post_b = w_alloc<float>(c, D); add_slot(c, vp + "post_layernorm.bias", {D}, SLOT_VEC, c->post_b, 0, 0.1f, 0.f);
+  c->post_w = w_alloc<float>(c, D); add_slot(c, vp + "post_layernorm.weight", {D}, SLOT_VEC, c->post_w, 0, 0.1, 1.f);
+  c->post_b = w_alloc<float>(c, D); add_slot(c, vp + "post_layernorm.bias", {D}, SLOT_VEC, c->post_b, 0, 0.1, 0.f);
 
   const int R = g.r_hidden, Fr = g.r_ffn, Q = g.r_queries, RL = g.r_layers;
   const std::string rp = "visual_resampler.";
-  c->rq = w_alloc<float>(c, (size_t)Q * R); add_slot(c, rp + "query_embeddding", {1, Q, R}, SLOT_VEC, c->rq, 0, 1.0f, 0.f);
+  c->rq = w_alloc<float>(c, (size_t)Q * R); add_slot(c, rp + "query_embeddding", {1, Q, R}, SLOT_VEC, c->rq, 0, 1.0, 0.f);
   c->r_wkv_all = w_alloc<bf16>(c, (size_t)RL * 2 * R * R);
   c->r_bkv_all = w_alloc<float>(c, (size_t)RL * 2 * R);
   c->rl.resize(RL);
@@ -204,45 +205,45 @@ void layout_weights(vcla_ctx* c) {
       // key/value additionally live in the all-layer [RL*2R, R] matrix used for the layer-invariant image rows
       void* d2w = (j > 0 && c->r_wkv_all) ? (void*)(c->r_wkv_all + ((size_t)i * 2 + (j - 1)) * R * R) : nullptr;
       void* d2b = (j > 0 && c->r_bkv_all) ? (void*)(c->r_bkv_all + ((size_t)i * 2 + (j - 1)) * R) : nullptr;
-      add_slot(c, lp + "crossattention.self." + pr[j] + ".weight", {R, R}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)j * R * R : nullptr, R, 1.5f / sqrtf((float)R), 0.f, LAY_PLAIN, 0, d2w);
-      add_slot(c, lp + "crossattention.self." + pr[j] + ".bias", {R}, SLOT_VEC, L.bqkv ? L.bqkv + j * R : nullptr, 0, 0.1f, 0.f, LAY_PLAIN, 0, d2b);
+      add_slot(c, lp + "crossattention.self." + pr[j] + ".weight", {R, R}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)j * R * R : nullptr, R, 1.5 / sqrt((double)R), 0.f, LAY_PLAIN, 0, d2w);
+      add_slot(c, lp + "crossattention.self." + pr[j] + ".bias", {R}, SLOT_VEC, L.bqkv ? L.bqkv + j * R : nullptr, 0, 0.1, 0.f, LAY_PLAIN, 0, d2b);
     }
-    L.wo = w_alloc<bf16>(c, (size_t)R * R); add_slot(c, lp + "crossattention.output.dense.weight", {R, R}, SLOT_MAT, L.wo, R, 1.0f / sqrtf((float)R), 0.f);
-    L.bo = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.dense.bias", {R}, SLOT_VEC, L.bo, 0, 0.05f, 0.f);
-    L.ln1_w = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.LayerNorm.weight", {R}, SLOT_VEC, L.ln1_w, 0, 0.1f, 1.f);
-    L.ln1_b = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.LayerNorm.bias", {R}, SLOT_VEC, L.ln1_b, 0, 0.1f, 0.f);
-    L.wi = w_alloc<bf16>(c, (size_t)Fr * R); add_slot(c, lp + "intermediate.dense.weight", {Fr, R}, SLOT_MAT, L.wi, R, 1.0f / sqrtf((float)R), 0.f);
-    L.bi = w_alloc<float>(c, Fr); add_slot(c, lp + "intermediate.dense.bias", {Fr}, SLOT_VEC, L.bi, 0, 0.1f, 0.f);
-    L.wo2 = w_alloc<bf16>(c, (size_t)R * Fr); add_slot(c, lp + "output.dense.weight", {R, Fr}, SLOT_MAT, L.wo2, Fr, 1.0f / sqrtf((float)Fr), 0.f);
-    L.bo2 = w_alloc<float>(c, R); add_slot(c, lp + "output.dense.bias", {R}, SLOT_VEC, L.bo2, 0, 0.05f, 0.f);
-    L.ln2_w = w_alloc<float>(c, R); add_slot(c, lp + "output.LayerNorm.weight", {R}, SLOT_VEC, L.ln2_w, 0, 0.1f, 1.f);
-    L.ln2_b = w_alloc<float>(c, R); add_slot(c, lp + "output.LayerNorm.bias", {R}, SLOT_VEC, L.ln2_b, 0, 0.1f, 0.f);
+    L.wo = w_alloc<bf16>(c, (size_t)R * R); add_slot(c, lp + "crossattention.output.dense.weight", {R, R}, SLOT_MAT, L.wo, R, 1.0 / sqrt((double)R), 0.f);
+    L.bo = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.dense.bias", {R}, SLOT_VEC, L.bo, 0, 0.05, 0.f);
+    L.ln1_w = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.LayerNorm.weight", {R}, SLOT_VEC, L.ln1_w, 0, 0.1, 1.f);
+    L.ln1_b = w_alloc<float>(c, R); add_slot(c, lp + "crossattention.output.LayerNorm.bias", {R}, SLOT_VEC, L.ln1_b, 0, 0.1, 0.f);
+    L.wi = w_alloc<bf16>(c, (size_t)Fr * R); add_slot(c, lp + "intermediate.dense.weight", {Fr, R}, SLOT_MAT, L.wi, R, 1.0 / sqrt((double)R), 0.f);
+    L.bi = w_alloc<float>(c, Fr); add_slot(c, lp + "intermediate.dense.bias", {Fr}, SLOT_VEC, L.bi, 0, 0.1, 0.f);
+    L.wo2 = w_alloc<bf16>(c, (size_t)R * Fr); add_slot(c, lp + "output.dense.weight", {R, Fr}, SLOT_MAT, L.wo2, Fr, 1.0 / sqrt((double)Fr), 0.f);
+    L.bo2 = w_alloc<float>(c, R); add_slot(c, lp + "output.dense.bias", {R}, SLOT_VEC, L.bo2, 0, 0.05, 0.f);
+    L.ln2_w = w_alloc<float>(c, R); add_slot(c, lp + "output.LayerNorm.weight", {R}, SLOT_VEC, L.ln2_w, 0, 0.1, 1.f);
+    L.ln2_b = w_alloc<float>(c, R); add_slot(c, lp + "output.LayerNorm.bias", {R}, SLOT_VEC, L.ln2_b, 0, 0.1, 0.f);
   }
   const int T = g.t_hidden, Ft = g.t_ffn, V = g.t_vocab, TL = g.t_layers;
-  c->proj_w = w_alloc<bf16>(c, (size_t)T * R); add_slot(c, "image_projection_layer.weight", {T, R}, SLOT_MAT, c->proj_w, R, 1.0f / sqrtf((float)R), 0.f);
-  c->proj_b = w_alloc<float>(c, T); add_slot(c, "image_projection_layer.bias", {T}, SLOT_VEC, c->proj_b, 0, 0.1f, 0.f);
+  c->proj_w = w_alloc<bf16>(c, (size_t)T * R); add_slot(c, "image_projection_layer.weight", {T, R}, SLOT_MAT, c->proj_w, R, 1.0 / sqrt((double)R), 0.f);
+  c->proj_b = w_alloc<float>(c, T); add_slot(c, "image_projection_layer.bias", {T}, SLOT_VEC, c->proj_b, 0, 0.1, 0.f);
 
   const std::string tp = "text_model.model.";
-  const float res_gain = 1.0f / sqrtf(2.0f * (float)TL);
-  c->embed = w_alloc<bf16>(c, (size_t)V * T); add_slot(c, tp + "embed_tokens.weight", {V, T}, SLOT_MAT, c->embed, T, 1.0f, 0.f);
+  const double res_gain = 1.0 / sqrt(2.0 * (double)TL);
+  c->embed = w_alloc<bf16>(c, (size_t)V * T); add_slot(c, tp + "embed_tokens.weight", {V, T}, SLOT_MAT, c->embed, T, 1.0, 0.f);
   c->tl.resize(TL);
   for (int i = 0; i < TL; ++i) {
     TextLayer& L = c->tl[i];
     const std::string lp = tp + "layers." + std::to_string(i) + ".";
-    L.ln1 = w_alloc<float>(c, T); add_slot(c, lp + "input_layernorm.weight", {T}, SLOT_VEC, L.ln1, 0, 0.1f, 1.f);
-    L.ln2 = w_alloc<float>(c, T); add_slot(c, lp + "post_attention_layernorm.weight", {T}, SLOT_VEC, L.ln2, 0, 0.1f, 1.f);
+    L.ln1 = w_alloc<float>(c, T); add_slot(c, lp + "input_layernorm.weight", {T}, SLOT_VEC, L.ln1, 0, 0.1, 1.f);
+    L.ln2 = w_alloc<float>(c, T); add_slot(c, lp + "post_attention_layernorm.weight", {T}, SLOT_VEC, L.ln2, 0, 0.1, 1.f);
     L.wqkv = w_alloc<bf16>(c, (size_t)3 * T * T);
-    add_slot(c, lp + "self_attn.q_proj.weight", {T, T}, SLOT_MAT, L.wqkv, T, 1.5f / sqrtf((float)T), 0.f);
-    add_slot(c, lp + "self_attn.k_proj.weight", {T, T}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)T * T : nullptr, T, 1.5f / sqrtf((float)T), 0.f);
-    add_slot(c, lp + "self_attn.v_proj.weight", {T, T}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)2 * T * T : nullptr, T, 1.0f / sqrtf((float)T), 0.f);
-    L.wo = w_alloc<bf16>(c, (size_t)T * T); add_slot(c, lp + "self_attn.o_proj.weight", {T, T}, SLOT_MAT, L.wo, T, res_gain * 2.0f / sqrtf((float)T), 0.f);
+    add_slot(c, lp + "self_attn.q_proj.weight", {T, T}, SLOT_MAT, L.wqkv, T, 1.5 / sqrt((double)T), 0.f);
+    add_slot(c, lp + "self_attn.k_proj.weight", {T, T}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)T * T : nullptr, T, 1.5 / sqrt((double)T), 0.f);
+    add_slot(c, lp + "self_attn.v_proj.weight", {T, T}, SLOT_MAT, L.wqkv ? L.wqkv + (size_t)2 * T * T : nullptr, T, 1.0 / sqrt((double)T), 0.f);
+    L.wo = w_alloc<bf16>(c, (size_t)T * T); add_slot(c, lp + "self_attn.o_proj.weight", {T, T}, SLOT_MAT, L.wo, T, res_gain * 2.0 / sqrt((double)T), 0.f);
     L.wgu = w_alloc<bf16>(c, (size_t)2 * Ft * T);
-    add_slot(c, lp + "mlp.gate_proj.weight", {Ft, T}, SLOT_MAT, L.wgu, T, 1.0f / sqrtf((float)T), 0.f, LAY_INTERLEAVE32, 0);
-    add_slot(c, lp + "mlp.up_proj.weight", {Ft, T}, SLOT_MAT, L.wgu, T, 1.0f / sqrtf((float)T), 0.f, LAY_INTERLEAVE32, 1);
-    L.wd = w_alloc<bf16>(c, (size_t)T * Ft); add_slot(c, lp + "mlp.down_proj.weight", {T, Ft}, SLOT_MAT, L.wd, Ft, res_gain * 4.0f / sqrtf((float)Ft), 0.f);
+    add_slot(c, lp + "mlp.gate_proj.weight", {Ft, T}, SLOT_MAT, L.wgu, T, 1.0 / sqrt((double)T), 0.f, LAY_INTERLEAVE32, 0);
+    add_slot(c, lp + "mlp.up_proj.weight", {Ft, T}, SLOT_MAT, L.wgu, T, 1.0 / sqrt((double)T), 0.f, LAY_INTERLEAVE32, 1);
+    L.wd = w_alloc<bf16>(c, (size_t)T * Ft); add_slot(c, lp + "mlp.down_proj.weight", {T, Ft}, SLOT_MAT, L.wd, Ft, res_gain * 4.0 / sqrt((double)Ft), 0.f);
   }
-  c->final_norm = w_alloc<float>(c, T); add_slot(c, tp + "norm.weight", {T}, SLOT_VEC, c->final_norm, 0, 0.1f, 1.f);
-  c->lm_head = w_alloc<bf16>(c, (size_t)V * T); add_slot(c, "text_model.lm_head.weight", {V, T}, SLOT_MAT, c->lm_head, T, 4.0f / sqrtf((float)T), 0.f);
+  c->final_norm = w_alloc<float>(c, T); add_slot(c, tp + "norm.weight", {T}, SLOT_VEC, c->final_norm, 0, 0.1, 1.f);
+  c->lm_head = w_alloc<bf16>(c, (size_t)V * T); add_slot(c, "text_model.lm_head.weight", {V, T}, SLOT_MAT, c->lm_head, T, 4.0 / sqrt((double)T), 0.f);
 }
 
 void layout_activations(vcla_ctx* c) {
@@ -388,6 +389,7 @@ void vcla_destroy(vcla_ctx* c) {
   if (c->a_arena) cudaFree(c->a_arena);
   if (c->kv_arena) cudaFree(c->kv_arena);
   if (c->staging) cudaFree(c->staging);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   delete c;
 }
 
@@ -486,7 +488,7 @@ int vcla_init_synthetic(vcla_ctx* c, uint32_t seed, vcla_stream stream) {
   for (const Slot& s : c->slots) {
     const int64_t n = s.rows * s.cols;
     const uint32_t sd = fnv1a32(s.name.c_str()) ^ (uint32_t)(seed * 0x9E3779B1u);
-    const float mul = (float)((double)s.std / sigma);
+    const float mul = (float)(s.std / sigma);
     if (s.kind == SLOT_VEC) {
       if (fill_hash_normal(nullptr, (float*)s.dst, n, sd, mul, s.mean, st)) return -1;
       if (s.dst2 && fill_hash_normal(nullptr, (float*)s.dst2, n, sd, mul, s.mean, st)) return -1;
@@ -677,10 +679,11 @@ int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, i
   if (it == c->graphs.end()) {
     const int64_t before = c->launches;
     cudaGraph_t graph = nullptr;
-    VCLA_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = decode_enqueue(c, tok_in, B, logits, tok_out, st);
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
-    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return -1; }
+    if (!c->cap_stream) VCLA_CUDA_OK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    VCLA_CUDA_OK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = decode_enqueue(c, tok_in, B, logits, tok_out, c->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return -1; }
     if (e != cudaSuccess) { set_error("decode: graph capture failed: %s", cudaGetErrorString(e)); return -1; }
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);

@@ -20,6 +20,7 @@ void set_pdl(bool on);
     cudaError_t _e = (expr);                                                                 \
     if (_e != cudaSuccess) {                                                                 \
       vcla::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (void)cudaGetLastError();                                                              \
       return -1;                                                                             \
     }                                                                                        \
   } while (0)

@@ -40,7 +40,7 @@ def gather_step_tokens(local_tok: torch.Tensor, global_batch: int, group=None) -
 
 @torch.no_grad()
 def generate_dp(model, input_ids: torch.Tensor, pixel_values: Optional[torch.Tensor], max_new_tokens: int, group=None,
-                step_hook: Optional[Callable] = None) -> torch.Tensor:
+                step_hook: Optional[Callable] = None, phase_hook: Optional[Callable] = None) -> torch.Tensor:
     """Greedy DP generation.  `input_ids` (B,T) / `pixel_values` (B,3,I,I) hold the GLOBAL batch on every rank;
     each rank computes only its slice.  Returns the (B, max_new_tokens) int64 tokens of the whole batch on every rank.
     `model` is a visualcla.VisualCLAModel (or any object with `._engine` and `._image_layout`)."""
@@ -51,8 +51,11 @@ def generate_dp(model, input_ids: torch.Tensor, pixel_values: Optional[torch.Ten
     lo, hi = shard_bounds(B, world, rank)
     eng = model._engine
     dev = eng.device
-    ids = input_ids[lo:hi]
-    px = None if pixel_values is None else pixel_values[lo:hi]
+    # slice first, then move: a rank only ever copies its own requests host -> device
+    ids = input_ids[lo:hi].to(dev, non_blocking=True)
+    px = None if pixel_values is None else pixel_values[lo:hi].to(dev, non_blocking=True)
+    if phase_hook is not None:
+        phase_hook("start")
     out = torch.empty(B, max_new_tokens, dtype=torch.int64, device=dev)
     nloc = hi - lo
     tok = torch.zeros(max(nloc, 1), dtype=torch.int32, device=dev)
@@ -62,10 +65,14 @@ def generate_dp(model, input_ids: torch.Tensor, pixel_values: Optional[torch.Ten
             eng.vision_encode(px)
         _, first, _ = eng.prefill(ids, mode, rows, all_logits=False, last_logits=False)
         tok[:nloc].copy_(first)
+    if phase_hook is not None:
+        phase_hook("prefill_done")
     for step in range(max_new_tokens):
         if step > 0 and nloc > 0:
             eng.decode_step(tok[:nloc], tok[:nloc], None)
         out[:, step] = gather_step_tokens(tok[:nloc], B, group)
         if step_hook is not None:
             step_hook(step)
+    if phase_hook is not None:
+        phase_hook("done")
     return out
