@@ -33,3 +33,19 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _device_hang_watchdog(request):
+    """A hung CUDA kernel blocks inside a C call where pytest-timeout cannot interrupt: dump the stack and exit instead
+    of burning GPU-box minutes."""
+    import faulthandler
+    if "gpu" not in request.keywords:
+        yield
+        return
+    limit = int(os.environ.get("VCLA_TEST_WATCHDOG", "420"))
+    faulthandler.dump_traceback_later(limit, exit=True)
+    try:
+        yield
+    finally:
+        faulthandler.cancel_dump_traceback_later()

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
 
   // ---- attention over cached tokens [t_begin, min(t_end, L)): 8 lanes per token, 16 dims per lane
   const int grp = lane >> 3, sub = lane & 7;
+  const uint32_t gmask = 0xffu << (grp * 8);
   float qreg[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) qreg[i] = s_q[sub * 16 + i];
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 
   const int c_end = min(t_end, L);
+  __syncwarp();
   for (int t = t_begin + warp * 4 + grp; t < c_end; t += 16) {
     const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + t / c.page_tokens);
     const int slot = t % c.page_tokens;
@@ -289,9 +291,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
       float2 kf = unpack_bf16x2(kw[i]);
       sc += qreg[2 * i] * kf.x + qreg[2 * i + 1] * kf.y;
     }
-    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    // the 4 token groups of a warp may run different trip counts: reduce with the group's own 8-lane mask
+    sc += __shfl_xor_sync(gmask, sc, 1);
+    sc += __shfl_xor_sync(gmask, sc, 2);
+    sc += __shfl_xor_sync(gmask, sc, 4);
     const float mn = fmaxf(m, sc);
     const float cr = __expf(m - mn), p = __expf(sc - mn);
     m = mn;
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
       acc[2 * i + 1] = acc[2 * i + 1] * cr + p * vf.y;
     }
   }
+  __syncwarp();
   // the new token (from smem), handled by warp 0 group 0 of the owning CTA
   if (owns_new && warp == 0 && grp == 0) {
     float sc = 0.f;
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = acc[i] * cr + p * s_v[sub * 16 + i];
   }
+  __syncwarp();
   // ---- merge the 4 token groups of a warp (lanes with equal `sub` hold the same dims)
 #pragma unroll
   for (int o = 8; o <= 16; o <<= 1) {
