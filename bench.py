@@ -129,7 +129,7 @@ def cpu_reference_sample(B, n_new, sample_B=2, decode_steps=2, threads=None):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import visualcla_oracle as O
-    threads = threads or os.cpu_count() or 1
+    threads = threads or O.pick_threads()     # os.cpu_count() threads is pathologically slow on the 128-cpu GPU box
     torch.set_num_threads(threads)
     cfg = O.PathConfig()
     if "w" not in _CPU_STATE:

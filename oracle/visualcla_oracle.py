@@ -34,6 +34,41 @@ import torch.nn.functional as F
 
 
 # --------------------------------------------------------------------------------------
+# host threads: torch's intra-op pool degrades badly when os.cpu_count() exceeds the cores this process
+# may actually use (observed: 128 "cpus" on the GPU box -> 30x slower than 8 threads) -> calibrate once
+# --------------------------------------------------------------------------------------
+_THREADS = None
+
+
+def pick_threads(candidates=(8, 16, 32, 64)) -> int:
+    """Set torch's intra-op thread count to the fastest of `candidates` for a 7B-shaped matmul; returns it."""
+    global _THREADS
+    if _THREADS is not None:
+        torch.set_num_threads(_THREADS)
+        return _THREADS
+    import os
+    import time
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    a, b = torch.randn(256, 4096), torch.randn(4096, 4096)
+    best, best_t = 1, float("inf")
+    for n in sorted({c for c in candidates if c <= avail} | {min(avail, 8)}):
+        torch.set_num_threads(n)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.95:
+            best, best_t = n, dt
+    _THREADS = best
+    torch.set_num_threads(best)
+    return best
+
+
+# --------------------------------------------------------------------------------------
 # configuration
 # --------------------------------------------------------------------------------------
 @dataclass

@@ -212,7 +212,7 @@ def test_config1_7b_logit_parity_gate():
     The oracle gets the device's own bf16 weights (vcla_read_weight), generated by the hash generator."""
     n_new = int(os.environ.get("VCLA_7B_STEPS", "24"))
     cfg = O.PathConfig()
-    torch.set_num_threads(os.cpu_count() or 8)
+    print(f"[7B parity] oracle host threads: {O.pick_threads()}")
 
     def dl(m):
         return {k: v.float() for k, v in m.state_dict().items()}

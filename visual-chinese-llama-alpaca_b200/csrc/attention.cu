@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   const int Sk = c.n0 + c.n1;
   const int off = Sk - c.Sq;  // causal: kv j visible to query i iff j <= i + off
 
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
 
   // ---- Q tile -> smem
   for (int i = tid; i < BQ * CHUNKS; i += 128) {
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = c.H * HD;
 
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
 
   const int L = c.seq_len[b];          // tokens already cached; the new token gets index L
   const int n = L + 1;

@@ -46,8 +46,8 @@ __global__ void layernorm_kernel(const float* x, int D, const float* __restrict_
                                  float eps, bf16* __restrict__ y_bf16, float* y_f32) {
   extern __shared__ float rowbuf[];
   __shared__ float red[32];
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const size_t row = blockIdx.x;
   const float* xr = x + row * D;
   float s = 0.f;
@@ -83,8 +83,8 @@ int layernorm(const float* x, int rows, int D, const float* w, const float* b, f
 __global__ void rmsnorm_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, float eps, bf16* __restrict__ y) {
   extern __shared__ float rowbuf[];
   __shared__ float red[32];
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const size_t row = blockIdx.x;
   const float* xr = x + row * D;
   float q = 0.f;
@@ -193,8 +193,8 @@ int embed_tokens(const int64_t* ids, int B, int T, int S, int D, const bf16* tab
   return 0;
 }
 __global__ void embed_tokens_i32_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ dst) {
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int b = blockIdx.x;
   int id = ids[b];
   if (id < 0 || id >= vocab) id = 0;
@@ -272,8 +272,8 @@ int rope_init(int max_pos, int head_dim, float theta) {
 __global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int HD, const float* __restrict__ rc, const float* __restrict__ rs,
                                       bf16* __restrict__ kv_pages, const int32_t* __restrict__ page_table, int pages_per_seq,
                                       int page_tokens, const int32_t* __restrict__ seq_base) {
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int s = blockIdx.x, b = blockIdx.y;
   const int T = H * HD, half = HD / 2;
   const int pos = (seq_base ? seq_base[b] : 0) + s;
@@ -315,8 +315,8 @@ __global__ void dec_resid_norm_kernel(const float* __restrict__ partial, int spl
                                       const float* __restrict__ w, float eps, bf16* __restrict__ xn) {
   extern __shared__ float rowbuf[];
   __shared__ float red[32];
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int b = blockIdx.x;
   float q = 0.f;
   for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
@@ -345,8 +345,8 @@ int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, 
 }
 
 __global__ void dec_silu_mul_kernel(const float* __restrict__ partial, int splits, int ws_rows, int F, bf16* __restrict__ h) {
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= F) return;
@@ -370,8 +370,8 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
                                   int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int b = blockIdx.y, ch = blockIdx.x;
   const int per = (V + kArgChunks - 1) / kArgChunks;
   const int v0 = ch * per, v1 = min(V, v0 + per);
@@ -405,8 +405,8 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
   }
 }
 __global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok) {
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int b = blockIdx.x, lane = threadIdx.x;
   float best = cand_val[b * kArgChunks + lane];
   int bi = cand_idx[b * kArgChunks + lane];
@@ -436,8 +436,8 @@ int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, in
 }
 
 __global__ void advance_seq_kernel(int32_t* seq_len, int B, int by) {
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  pdl_launch_dependents();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) seq_len[b] += by;
 }

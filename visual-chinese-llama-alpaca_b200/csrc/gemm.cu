@@ -125,8 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // everything above overlaps the tail of the previous kernel when launched with PDL
-  pdl_wait();
+  // PDL: let the next kernel's CTAs become resident as soon as ours are (they only prefetch read-only weights and
+  // then block in griddepcontrol.wait until this grid has completed), see the producer below.
   pdl_launch_dependents();
 
   auto tile_coords = [&](int t, int& m_blk, int& n_blk, int& kb0, int& kb1, int& ks) {
@@ -141,8 +141,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
+      // The weight operand (A when swap-AB, else B) never depends on the previous kernel, so its tiles for the first
+      // STAGES pipeline slots are requested BEFORE griddepcontrol.wait: weight streaming from HBM continues across
+      // kernel boundaries.  The activation operand is loaded only after the dependency has resolved.
       int stage = 0;
       uint32_t phase = 0;
+      bool dep_ready = false;
+      int npend = 0;
+      uint32_t pend_dst[STAGES], pend_bar[STAGES];
+      int pend_c0[STAGES], pend_c1[STAGES];
+      const CUtensorMap* act_map = SWAP ? &tmB : &tmA;
+      const uint64_t act_policy = SWAP ? p.policy_b : p.policy_a;
+      auto flush_pending = [&]() {
+        pdl_wait();
+        for (int i = 0; i < npend; ++i) tma_load_2d(pend_dst[i], act_map, pend_c0[i], pend_c1[i], pend_bar[i], act_policy);
+        npend = 0;
+        dep_ready = true;
+      };
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int m_blk, n_blk, kb0, kb1, ks;
         tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
@@ -150,11 +165,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * kBlockM, full_bar(stage), p.policy_a);
-          tma_load_2d(sa + C::A_BYTES, &tmB, kb * kBlockK, n_blk * BN, full_bar(stage), p.policy_b);
+          if constexpr (SWAP) {
+            tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * kBlockM, full_bar(stage), p.policy_a);           // weights
+            if (dep_ready) {
+              tma_load_2d(sa + C::A_BYTES, &tmB, kb * kBlockK, n_blk * BN, full_bar(stage), p.policy_b);
+            } else {
+              pend_dst[npend] = sa + C::A_BYTES; pend_bar[npend] = full_bar(stage); pend_c0[npend] = kb * kBlockK; pend_c1[npend] = n_blk * BN; ++npend;
+            }
+          } else {
+            tma_load_2d(sa + C::A_BYTES, &tmB, kb * kBlockK, n_blk * BN, full_bar(stage), p.policy_b);   // weights
+            if (dep_ready) {
+              tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * kBlockM, full_bar(stage), p.policy_a);
+            } else {
+              pend_dst[npend] = sa; pend_bar[npend] = full_bar(stage); pend_c0[npend] = kb * kBlockK; pend_c1[npend] = m_blk * kBlockM; ++npend;
+            }
+          }
+          if (!dep_ready && npend == STAGES) flush_pending();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (!dep_ready) flush_pending();
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -195,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue warps =====================
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
+    pdl_wait();                            // outputs / residual reads are ordered after the previous grid
     int acc = 0;
     uint32_t accphase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {

@@ -72,6 +72,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("VCLA_PDL", "") not in ("", "0"):
+        lib.vcla_set_pdl(1)        # programmatic dependent launch for every kernel enqueued afterwards
     _lib = lib
     return lib
 
