@@ -140,6 +140,34 @@ def case_resampler_fullwidth(visualcla, seed=3):
     print(f"[golden] resampler_fullwidth: out {tuple(y.shape)} absmax {float(y.abs().max()):.3f}")
 
 
+def case_host_logic(visualcla):
+    """Prompt strings (ref: modeling_utils.py:49-80) and the extra samplers (ref: :250-320) for the host-side tests."""
+    import json
+    from visualcla import modeling_utils as mu
+
+    class Tok:
+        bos_token, img_start_token, img_end_token, img_token = "<s>", "<img>", "</img>", "<img_token>"
+
+        def __call__(self, text, return_tensors=None, add_special_tokens=None):
+            return text
+
+    h0 = []
+    h1 = [{"type": "instruction", "value": "What is in the picture?", "first_instruction": True},
+          {"type": "response", "value": " A cat."}]
+    h2 = h1 + [{"type": "instruction", "value": "What colour?"}, {"type": "response", "value": " Black and white."}]
+    cases = []
+    for hist, text, n in ((h0, "Describe the image.", 64), (h1, "And the background?", 64), (h2, "Thanks!", 8)):
+        cases.append({"history": hist, "text": text, "num_patch": n, "prompt": mu.encoding_text(hist, text, n, Tok())})
+    with open(os.path.join(OUT, "prompts.json"), "w") as f:
+        json.dump(cases, f, ensure_ascii=False, indent=1)
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(3, 500, generator=g) * 3.0
+    tfs = mu.TailFreeLogitsWarper(tfs=0.9)(None, logits.clone())
+    topa = mu.TopALogitsWarper(top_a=0.2)(None, logits.clone())
+    np.savez_compressed(os.path.join(OUT, "samplers.npz"), logits=logits.numpy(), tfs_0p9=tfs.numpy(), top_a_0p2=topa.numpy())
+    print(f"[golden] host logic: {len(cases)} prompts; tfs keeps {int(torch.isfinite(tfs).sum())}, top_a keeps {int(torch.isfinite(topa).sum())}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -147,6 +175,7 @@ def main():
     case_tiny(visualcla, "tiny_b2_t12", seed=0, batch=2, t_text=12, n_new=8)
     case_tiny(visualcla, "tiny_b3_t7", seed=1, batch=3, t_text=7, n_new=5)
     case_resampler_fullwidth(visualcla)
+    case_host_logic(visualcla)
 
 
 if __name__ == "__main__":
