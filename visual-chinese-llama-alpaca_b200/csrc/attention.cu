@@ -207,60 +207,68 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
 // =================================================================================================
 // decode (hd = 128): grid (kv_splits, H, B), 128 threads
 // =================================================================================================
-__global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
-                                                          const float* __restrict__ rope_sin) {
+constexpr int kDecWarps = 8;   // 256 threads: 32 cached tokens in flight per CTA iteration
+__global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+                                                                     const float* __restrict__ rope_sin) {
   constexpr int HD = 128;
   __shared__ float s_q[HD];
   __shared__ float s_k[HD];
   __shared__ float s_v[HD];
-  __shared__ float s_acc[4][HD];
-  __shared__ float s_m[4], s_l[4];
+  __shared__ float s_acc[kDecWarps][HD];
+  __shared__ float s_m[kDecWarps], s_l[kDecWarps];
   __shared__ int s_last;
 
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = c.H * HD;
 
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_launch_dependents();
   pdl_wait();
 
   const int L = c.seq_len[b];          // tokens already cached; the new token gets index L
   const int n = L + 1;
   int chunk = (n + c.kv_splits - 1) / c.kv_splits;
-  chunk = (chunk + 15) & ~15;
+  chunk = (chunk + 31) & ~31;
   const int t_begin = split * chunk;
   const int t_end = min(n, t_begin + chunk);
   const bool owns_new = (t_begin <= L) && (L < t_end);
 
   // ---- reduce the split-K partials of this head's q (and k, v if this CTA owns the new token); RoPE
   {
-    const int d = tid;
+    const int d = tid & (HD - 1);
     float qv = 0.f, kv = 0.f, vv = 0.f;
-    for (int s = 0; s < c.splits; ++s) {
-      const float* row = c.qkv_partial + ((size_t)s * c.ws_rows + b) * (size_t)(3 * T);
-      qv += row[h * HD + d];
-      if (owns_new) { kv += row[T + h * HD + d]; vv += row[2 * T + h * HD + d]; }
+    if (tid < HD) {
+      for (int s = 0; s < c.splits; ++s) {
+        const float* row = c.qkv_partial + ((size_t)s * c.ws_rows + b) * (size_t)(3 * T);
+        qv += __ldcg(row + h * HD + d);
+        if (owns_new) { kv += __ldcg(row + T + h * HD + d); vv += __ldcg(row + 2 * T + h * HD + d); }
+      }
+      s_q[d] = qv; s_k[d] = kv; s_v[d] = vv;
     }
-    s_q[d] = qv; s_k[d] = kv; s_v[d] = vv;
     __syncthreads();
-    const float cs = rope_cos[(size_t)L * (HD / 2) + (d & 63)], sn = rope_sin[(size_t)L * (HD / 2) + (d & 63)];
-    const float qp = (d < 64) ? -s_q[d + 64] : s_q[d - 64];
-    const float kp = (d < 64) ? -s_k[d + 64] : s_k[d - 64];
-    const float qr = (qv * cs + qp * sn) * c.scale;
-    const float kr = kv * cs + kp * sn;
+    float qr = 0.f, kr = 0.f;
+    if (tid < HD) {
+      const float cs = rope_cos[(size_t)L * (HD / 2) + (d & 63)], sn = rope_sin[(size_t)L * (HD / 2) + (d & 63)];
+      const float qp = (d < 64) ? -s_q[d + 64] : s_q[d - 64];
+      const float kp = (d < 64) ? -s_k[d + 64] : s_k[d - 64];
+      qr = (qv * cs + qp * sn) * c.scale;
+      kr = kv * cs + kp * sn;
+    }
     __syncthreads();
-    s_q[d] = qr;
-    if (owns_new) {
-      // the cache holds bf16; attend over the same rounded values every later step will read
-      const bf16 kb = __float2bfloat16(kr), vb = __float2bfloat16(vv);
-      s_k[d] = __bfloat162float(kb);
-      s_v[d] = __bfloat162float(vb);
-      const int page = c.page_table[(size_t)b * c.pages_per_seq + L / c.page_tokens];
-      const int slot = L % c.page_tokens;
-      bf16* kdst = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD;
-      bf16* vdst = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * c.page_tokens + slot) * HD;
-      kdst[d] = kb;
-      vdst[d] = vb;
+    if (tid < HD) {
+      s_q[d] = qr;
+      if (owns_new) {
+        // the cache holds bf16; attend over the same rounded values every later step will read
+        const bf16 kb = __float2bfloat16(kr), vb = __float2bfloat16(vv);
+        s_k[d] = __bfloat162float(kb);
+        s_v[d] = __bfloat162float(vb);
+        const int page = c.page_table[(size_t)b * c.pages_per_seq + L / c.page_tokens];
+        const int slot = L % c.page_tokens;
+        bf16* kdst = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD;
+        bf16* vdst = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * c.page_tokens + slot) * HD;
+        kdst[d] = kb;
+        vdst[d] = vb;
+      }
     }
     __syncthreads();
   }
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
 
   const int c_end = min(t_end, L);
   __syncwarp();
-  for (int t = t_begin + warp * 4 + grp; t < c_end; t += 16) {
+  for (int t = t_begin + warp * 4 + grp; t < c_end; t += kDecWarps * 4) {
     const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + t / c.page_tokens);
     const int slot = t % c.page_tokens;
     const uint4* kp = reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
@@ -343,22 +351,26 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
     if (sub == 0) { s_m[warp] = m; s_l[warp] = l; }
   }
   __syncthreads();
-  // ---- merge the 4 warps: thread d owns output dim d
-  float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-  float Lsum = 0.f, O = 0.f;
+  // ---- merge the warps: thread d (< 128) owns output dim d
+  float M = -INFINITY;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    const float cw = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
-    Lsum += s_l[w] * cw;
-    O += s_acc[w][tid] * cw;
+  for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, s_m[w]);
+  float Lsum = 0.f, O = 0.f;
+  if (tid < HD) {
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) {
+      const float cw = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
+      Lsum += s_l[w] * cw;
+      O += s_acc[w][tid] * cw;
+    }
   }
   if (c.kv_splits == 1) {
-    c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(O / Lsum);
+    if (tid < HD) c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(O / Lsum);
     return;
   }
   // ---- cross-CTA combine: publish partial, last arriver reduces in fixed split order
   float* sp = c.scratch + (((size_t)b * c.H + h) * c.kv_splits + split) * (HD + 2);
-  sp[tid] = O;
+  if (tid < HD) sp[tid] = O;
   if (tid == 0) { sp[HD] = M; sp[HD + 1] = Lsum; }
   __threadfence();
   __syncthreads();
@@ -369,17 +381,19 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const DecodeAttnCall c
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const float* base = c.scratch + ((size_t)b * c.H + h) * c.kv_splits * (HD + 2);
-  float Mg = -INFINITY;
-  for (int s = 0; s < c.kv_splits; ++s) Mg = fmaxf(Mg, __ldcg(base + (size_t)s * (HD + 2) + HD));
-  float Lg = 0.f, Og = 0.f;
-  for (int s = 0; s < c.kv_splits; ++s) {
-    const float ms = __ldcg(base + (size_t)s * (HD + 2) + HD);
-    const float cw = (ms == -INFINITY) ? 0.f : __expf(ms - Mg);
-    Lg += __ldcg(base + (size_t)s * (HD + 2) + HD + 1) * cw;
-    Og += __ldcg(base + (size_t)s * (HD + 2) + tid) * cw;
+  if (tid < HD) {
+    const float* base = c.scratch + ((size_t)b * c.H + h) * c.kv_splits * (HD + 2);
+    float Mg = -INFINITY;
+    for (int s = 0; s < c.kv_splits; ++s) Mg = fmaxf(Mg, __ldcg(base + (size_t)s * (HD + 2) + HD));
+    float Lg = 0.f, Og = 0.f;
+    for (int s = 0; s < c.kv_splits; ++s) {
+      const float ms = __ldcg(base + (size_t)s * (HD + 2) + HD);
+      const float cw = (ms == -INFINITY) ? 0.f : __expf(ms - Mg);
+      Lg += __ldcg(base + (size_t)s * (HD + 2) + HD + 1) * cw;
+      Og += __ldcg(base + (size_t)s * (HD + 2) + tid) * cw;
+    }
+    c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(Og / Lg);
   }
-  c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(Og / Lg);
   if (tid == 0) c.counters[b * c.H + h] = 0;  // ready for the next step / graph replay
 }
 
@@ -391,7 +405,7 @@ int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   if (c.HD != 128) { set_error("attention_decode: head dim %d unsupported (128)", c.HD); return -1; }
   if (rope_cos_table() == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(kDecWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;
   if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }

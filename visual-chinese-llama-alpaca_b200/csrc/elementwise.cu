@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <vector>
 
@@ -268,35 +269,51 @@ int rope_init(int max_pos, int head_dim, float theta) {
   return 0;
 }
 
-// prefill: rotate q,k in place inside the fused [B*S, 3T] projection buffer; append k,v to the paged cache
+// prefill: rotate q,k in place inside the fused [B*S, 3T] projection buffer; append k,v to the paged cache.
+// One CTA per token; each thread owns 8 consecutive rotary pairs of one head: 128-bit loads/stores throughout.
 __global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int HD, const float* __restrict__ rc, const float* __restrict__ rs,
                                       bf16* __restrict__ kv_pages, const int32_t* __restrict__ page_table, int pages_per_seq,
                                       int page_tokens, const int32_t* __restrict__ seq_base) {
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
   const int s = blockIdx.x, b = blockIdx.y;
-  const int T = H * HD, half = HD / 2;
+  const int T = H * HD, half = HD / 2, groups = half / 8;
   const int pos = (seq_base ? seq_base[b] : 0) + s;
   bf16* row = qkv + ((size_t)b * S + s) * 3 * T;
   const int page = page_table[(size_t)b * pages_per_seq + pos / page_tokens];
   const int slot = pos % page_tokens;
-  // one thread per (head, i<half) pair
-  for (int idx = threadIdx.x; idx < H * half; idx += blockDim.x) {
-    const int h = idx / half, i = idx % half;
-    const float c = rc[(size_t)pos * half + i], sn = rs[(size_t)pos * half + i];
-    bf16* q = row + h * HD;
-    bf16* k = row + T + h * HD;
-    const bf16* v = row + 2 * T + h * HD;
-    float q1 = __bfloat162float(q[i]), q2 = __bfloat162float(q[i + half]);
-    float k1 = __bfloat162float(k[i]), k2 = __bfloat162float(k[i + half]);
-    const bf16 qo1 = __float2bfloat16(q1 * c - q2 * sn), qo2 = __float2bfloat16(q2 * c + q1 * sn);
-    const bf16 ko1 = __float2bfloat16(k1 * c - k2 * sn), ko2 = __float2bfloat16(k2 * c + k1 * sn);
-    q[i] = qo1; q[i + half] = qo2;
-    k[i] = ko1; k[i + half] = ko2;
+  for (int idx = threadIdx.x; idx < H * groups; idx += blockDim.x) {
+    const int h = idx / groups, i = (idx % groups) * 8;
+    float cs[8], sn[8];
+    *reinterpret_cast<float4*>(cs) = *reinterpret_cast<const float4*>(rc + (size_t)pos * half + i);
+    *reinterpret_cast<float4*>(cs + 4) = *reinterpret_cast<const float4*>(rc + (size_t)pos * half + i + 4);
+    *reinterpret_cast<float4*>(sn) = *reinterpret_cast<const float4*>(rs + (size_t)pos * half + i);
+    *reinterpret_cast<float4*>(sn + 4) = *reinterpret_cast<const float4*>(rs + (size_t)pos * half + i + 4);
     bf16* kd = kv_pages + ((((size_t)page * 2 + 0) * H + h) * page_tokens + slot) * HD;
     bf16* vd = kv_pages + ((((size_t)page * 2 + 1) * H + h) * page_tokens + slot) * HD;
-    kd[i] = ko1; kd[i + half] = ko2;
-    vd[i] = v[i]; vd[i + half] = v[i + half];
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {   // 0: q, 1: k
+      bf16* x = row + which * T + h * HD;
+      const uint4 lo = *reinterpret_cast<const uint4*>(x + i), hi = *reinterpret_cast<const uint4*>(x + i + half);
+      const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+      uint32_t ol[4], oh[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(lw[j]), c2 = unpack_bf16x2(hw[j]);
+        ol[j] = pack_bf16x2(a.x * cs[2 * j] - c2.x * sn[2 * j], a.y * cs[2 * j + 1] - c2.y * sn[2 * j + 1]);
+        oh[j] = pack_bf16x2(c2.x * cs[2 * j] + a.x * sn[2 * j], c2.y * cs[2 * j + 1] + a.y * sn[2 * j + 1]);
+      }
+      const uint4 vlo = make_uint4(ol[0], ol[1], ol[2], ol[3]), vhi = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      *reinterpret_cast<uint4*>(x + i) = vlo;
+      *reinterpret_cast<uint4*>(x + i + half) = vhi;
+      if (which == 1) {
+        *reinterpret_cast<uint4*>(kd + i) = vlo;
+        *reinterpret_cast<uint4*>(kd + i + half) = vhi;
+      }
+    }
+    const bf16* v = row + 2 * T + h * HD;
+    *reinterpret_cast<uint4*>(vd + i) = *reinterpret_cast<const uint4*>(v + i);
+    *reinterpret_cast<uint4*>(vd + i + half) = *reinterpret_cast<const uint4*>(v + i + half);
   }
 }
 int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table, int pages_per_seq,
@@ -311,36 +328,60 @@ int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv
 // ------------------------------------------------------------------------------------------------
 // decode consumers of split-K partial sums
 // ------------------------------------------------------------------------------------------------
-__global__ void dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows, float* __restrict__ resid, int D,
-                                      const float* __restrict__ w, float eps, bf16* __restrict__ xn) {
-  extern __shared__ float rowbuf[];
+// One 8-CTA thread-block cluster per batch row: each CTA reduces the split-K partials of D/8 columns into the fp32
+// residual stream, the row's sum of squares is exchanged through distributed shared memory, then every CTA writes its
+// slice of the normalised bf16 GEMM operand.  (One CTA per row was latency-bound: 12 us per launch, 65 launches/step.)
+constexpr int kNormCluster = 8;
+__global__ void __cluster_dims__(kNormCluster, 1, 1) __launch_bounds__(128)
+dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows, float* __restrict__ resid, int D,
+                      const float* __restrict__ w, float eps, bf16* __restrict__ xn) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[32];
+  __shared__ float s_part;
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
+  const int chunk = D / kNormCluster;
+  const int c0 = blockIdx.x * chunk;
+  constexpr int MAXV = 4;
+  float4 vals[MAXV];
   float q = 0.f;
-  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
-    float4 v = *reinterpret_cast<const float4*>(resid + (size_t)b * D + i);
+  int nv = 0;
+  for (int i = threadIdx.x * 4; i < chunk; i += blockDim.x * 4, ++nv) {
+    const int col = c0 + i;
+    float4 v = *reinterpret_cast<const float4*>(resid + (size_t)b * D + col);
     if (partial) {
+#pragma unroll 4
       for (int s = 0; s < splits; ++s) {
-        float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)s * ws_rows + b) * D + i);
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * ws_rows + b) * D + col));
         v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
       }
-      *reinterpret_cast<float4*>(resid + (size_t)b * D + i) = v;
+      *reinterpret_cast<float4*>(resid + (size_t)b * D + col) = v;
     }
-    *reinterpret_cast<float4*>(rowbuf + i) = v;
+    vals[nv] = v;
     q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
-  const float rstd = rsqrtf(block_sum(q, red) / D + eps);
-  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
-    float4 v = *reinterpret_cast<float4*>(rowbuf + i);
-    float4 wv = *reinterpret_cast<const float4*>(w + i);
-    *reinterpret_cast<uint2*>(xn + (size_t)b * D + i) =
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) s_part = q;
+  cluster.sync();
+  float tot = 0.f;
+#pragma unroll
+  for (int r = 0; r < kNormCluster; ++r) tot += *cluster.map_shared_rank(&s_part, r);
+  cluster.sync();            // nobody may exit while a peer still reads its shared memory
+  const float rstd = rsqrtf(tot / D + eps);
+  nv = 0;
+  for (int i = threadIdx.x * 4; i < chunk; i += blockDim.x * 4, ++nv) {
+    const int col = c0 + i;
+    const float4 v = vals[nv];
+    const float4 wv = *reinterpret_cast<const float4*>(w + col);
+    *reinterpret_cast<uint2*>(xn + (size_t)b * D + col) =
         make_uint2(pack_bf16x2(v.x * rstd * wv.x, v.y * rstd * wv.y), pack_bf16x2(v.z * rstd * wv.z, v.w * rstd * wv.w));
   }
 }
 int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, int B, int D, const float* w, float eps, bf16* xn, cudaStream_t st) {
-  VCLA_LAUNCH(dec_resid_norm_kernel, dim3(B), dim3(D >= 2048 ? 512 : 128), (size_t)D * 4, st, partial, splits, ws_rows, resid, D, w, eps, xn);
+  if (D % (kNormCluster * 4) != 0 || D / kNormCluster > 128 * 4 * 4) { set_error("dec_resid_norm: unsupported D %d", D); return -1; }
+  VCLA_LAUNCH(dec_resid_norm_kernel, dim3(kNormCluster, B), dim3(128), 0, st, partial, splits, ws_rows, resid, D, w, eps, xn);
   return 0;
 }
 

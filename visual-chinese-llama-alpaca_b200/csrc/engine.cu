@@ -293,7 +293,7 @@ void layout_activations(vcla_ctx* c) {
 int pick_splits(int n_out, int K) {
   const int tiles = (n_out + 127) / 128;
   const int kb = (K + 63) / 64;
-  const int target = 2 * 148 * 2;
+  const int target = 148 * 2;   // one wave of the persistent 2-CTA/SM grid; more splits only inflate the consumers' work
   int s = (target + tiles - 1) / tiles;
   int max_s = kb / 8; if (max_s < 1) max_s = 1;
   if (s > max_s) s = max_s;
