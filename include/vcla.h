@@ -142,6 +142,11 @@ int vcla_op_rmsnorm(const float* x, int rows, int D, const float* w, float eps, 
  * 4 lm_head) over every layer's distinct weights with batch B, timed with CUDA events on `stream`; returns the mean
  * microseconds per kernel launch and the algorithmic weight bytes one launch streams.  Synchronises. */
 int vcla_bench_decode_gemm(vcla_ctx* ctx, int which, int B, int reps, float* avg_us, int64_t* weight_bytes, vcla_stream stream);
+/* Timeline trace for profiles/: when enabled, CTA (0,0,0) of every kernel appends {tag, t_entry, t_dependency_resolved, t_exit}
+ * (%globaltimer, ns).  Tags: 1 swap-AB GEMM, 2 GEMM, 3 prefill attention, 4 decode attention, 5 layernorm, 6 rmsnorm, 7 rope+cache,
+ * 8 resid+rmsnorm, 9 silu*mul, 10/11 logits+argmax, 12 advance, 13 embed.  vcla_trace_read synchronises and clears. */
+int vcla_trace_enable(vcla_ctx* ctx, int max_events);
+int vcla_trace_read(vcla_ctx* ctx, uint64_t* dst_host, int max_events, int* n_events);
 /* enable/disable programmatic dependent launch for subsequently enqueued kernels (process-wide) */
 void vcla_set_pdl(int on);
 

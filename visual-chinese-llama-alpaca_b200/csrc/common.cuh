@@ -178,6 +178,38 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// Optional timeline trace (debug / profiles): CTA (0,0,0) thread 0 of every kernel records globaltimer at entry, after
+// its dependency wait and at exit.  Off unless the host installs a buffer (vcla_trace_enable).
+// ------------------------------------------------------------------------------------------------
+struct TraceBuf { unsigned long long count; unsigned long long ev[1]; };   // ev: [tag, t_entry, t_dep, t_exit] x N
+static __device__ TraceBuf* g_trace = nullptr;
+static __device__ unsigned long long g_trace_cap = 0;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long* slot;
+  __device__ __forceinline__ TraceScope(int tag) : slot(nullptr) {
+    if (g_trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      const unsigned long long t = gtime();
+      const unsigned long long i = atomicAdd(&g_trace->count, 1ull);
+      if (i < g_trace_cap) { slot = g_trace->ev + 4 * i; slot[0] = (unsigned long long)tag; slot[1] = t; slot[2] = 0; slot[3] = 0; }
+    }
+  }
+  __device__ __forceinline__ void dep() { if (slot) slot[2] = gtime(); }
+  __device__ __forceinline__ void done() { if (slot) slot[3] = gtime(); }
+};
+#define VCLA_DEFINE_TRACE_SETTER(fn)                                                       \
+  int fn(void* buf, unsigned long long cap) {                                              \
+    vcla::TraceBuf* b = reinterpret_cast<vcla::TraceBuf*>(buf);                            \
+    if (cudaMemcpyToSymbol(vcla::g_trace, &b, sizeof(b)) != cudaSuccess) return -1;        \
+    if (cudaMemcpyToSymbol(vcla::g_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return -1; \
+    return 0;                                                                              \
+  }
+
+// ------------------------------------------------------------------------------------------------
 // legacy tensor path used by the small attention kernels (mma.sync m16n8k16 bf16) + ldmatrix + cp.async
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

@@ -47,8 +47,10 @@ __global__ void layernorm_kernel(const float* x, int D, const float* __restrict_
                                  float eps, bf16* __restrict__ y_bf16, float* y_f32) {
   extern __shared__ float rowbuf[];
   __shared__ float red[32];
+  TraceScope trace(5);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const size_t row = blockIdx.x;
   const float* xr = x + row * D;
   float s = 0.f;
@@ -84,8 +86,10 @@ int layernorm(const float* x, int rows, int D, const float* w, const float* b, f
 __global__ void rmsnorm_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, float eps, bf16* __restrict__ y) {
   extern __shared__ float rowbuf[];
   __shared__ float red[32];
+  TraceScope trace(6);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const size_t row = blockIdx.x;
   const float* xr = x + row * D;
   float q = 0.f;
@@ -194,8 +198,10 @@ int embed_tokens(const int64_t* ids, int B, int T, int S, int D, const bf16* tab
   return 0;
 }
 __global__ void embed_tokens_i32_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ dst) {
+  TraceScope trace(13);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int b = blockIdx.x;
   int id = ids[b];
   if (id < 0 || id >= vocab) id = 0;
@@ -274,8 +280,10 @@ int rope_init(int max_pos, int head_dim, float theta) {
 __global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int HD, const float* __restrict__ rc, const float* __restrict__ rs,
                                       bf16* __restrict__ kv_pages, const int32_t* __restrict__ page_table, int pages_per_seq,
                                       int page_tokens, const int32_t* __restrict__ seq_base) {
+  TraceScope trace(7);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int s = blockIdx.x, b = blockIdx.y;
   const int T = H * HD, half = HD / 2, groups = half / 8;
   const int pos = (seq_base ? seq_base[b] : 0) + s;
@@ -339,8 +347,10 @@ dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[32];
   __shared__ float s_part;
+  TraceScope trace(8);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int b = blockIdx.y;
   const int chunk = D / kNormCluster;
   const int c0 = blockIdx.x * chunk;
@@ -386,8 +396,10 @@ int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, 
 }
 
 __global__ void dec_silu_mul_kernel(const float* __restrict__ partial, int splits, int ws_rows, int F, bf16* __restrict__ h) {
+  TraceScope trace(9);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= F) return;
@@ -411,8 +423,10 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
                                   int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
   __shared__ float sv[32];
   __shared__ int si[32];
+  TraceScope trace(10);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int b = blockIdx.y, ch = blockIdx.x;
   const int per = (V + kArgChunks - 1) / kArgChunks;
   const int v0 = ch * per, v1 = min(V, v0 + per);
@@ -446,8 +460,10 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
   }
 }
 __global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok) {
+  TraceScope trace(11);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int b = blockIdx.x, lane = threadIdx.x;
   float best = cand_val[b * kArgChunks + lane];
   int bi = cand_idx[b * kArgChunks + lane];
@@ -477,8 +493,10 @@ int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, in
 }
 
 __global__ void advance_seq_kernel(int32_t* seq_len, int B, int by) {
+  TraceScope trace(12);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
+  trace.dep();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) seq_len[b] += by;
 }
@@ -556,5 +574,7 @@ int interleave_rows32(const bf16* src, int rows, int cols, int which, bf16* dst,
   VCLA_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+VCLA_DEFINE_TRACE_SETTER(trace_set_elementwise)
 
 }  // namespace vcla

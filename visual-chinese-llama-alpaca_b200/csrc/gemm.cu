@@ -105,6 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  TraceScope trace(SWAP ? 1 : 2);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -154,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint64_t act_policy = SWAP ? p.policy_b : p.policy_a;
       auto flush_pending = [&]() {
         pdl_wait();
+        trace.dep();
         for (int i = 0; i < npend; ++i) tma_load_2d(pend_dst[i], act_map, pend_c0[i], pend_c1[i], pend_bar[i], act_policy);
         npend = 0;
         dep_ready = true;
@@ -370,8 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  trace.done();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
+
+VCLA_DEFINE_TRACE_SETTER(trace_set_gemm)
 
 // ------------------------------------------------------------------------------------------------
 // host side

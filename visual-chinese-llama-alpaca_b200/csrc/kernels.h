@@ -63,6 +63,9 @@ int gemm_tc(const GemmCall& c, cudaStream_t st);
 // correctness reference for the tests only (CUDA-core, one thread per output)
 int gemm_naive(const GemmCall& c, cudaStream_t st);
 int gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
+int trace_set_gemm(void* buf, unsigned long long cap);
+int trace_set_attention(void* buf, unsigned long long cap);
+int trace_set_elementwise(void* buf, unsigned long long cap);
 
 // ------------------------------------------------------------------------------------------
 // attention

@@ -54,6 +54,8 @@ _SIGNATURES = [
     ("vcla_op_layernorm", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
     ("vcla_op_rmsnorm", C.c_int, [_P, C.c_int, C.c_int, _P, C.c_float, _P, _P]),
     ("vcla_bench_decode_gemm", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P]),
+    ("vcla_trace_enable", C.c_int, [_P, C.c_int]),
+    ("vcla_trace_read", C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     ("vcla_set_pdl", None, [C.c_int]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

@@ -163,6 +163,18 @@ class Engine:
             N.check(self.lib.vcla_bench_decode_gemm(self._ctx, which, B, reps, C.byref(us), C.byref(nbytes), self._stream()), "vcla_bench_decode_gemm")
         return us.value, nbytes.value
 
+    def trace_enable(self, max_events: int = 4096):
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_trace_enable(self._ctx, max_events), "vcla_trace_enable")
+
+    def trace_read(self, max_events: int = 4096):
+        """-> list of (tag, t_entry_ns, t_dep_ns, t_exit_ns) recorded since the last read."""
+        buf = torch.zeros(max_events, 4, dtype=torch.int64)
+        n = C.c_int()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_trace_read(self._ctx, N.ptr(buf), max_events, C.byref(n)), "vcla_trace_read")
+        return [tuple(int(x) for x in row) for row in buf[: n.value].tolist()]
+
     def read_stage(self, stage: str, B: int) -> torch.Tensor:
         c = self.path_cfg
         shapes = {"vit_out": (B, (c["v_image"] // c["v_patch"]) ** 2 + 1, c["v_hidden"]),
