@@ -214,7 +214,7 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    _native.load().vcla_set_pdl(args.pdl)
+    _native.load().vcla_set_pdl(1 if args.pdl else 0)
     Bl, B, n_new = args.batch_per_gpu, args.batch_per_gpu * world, args.new_tokens
     max_seq = S_PREFILL + n_new + 1
     model = visualcla.VisualCLAModel.from_synthetic("7b", seed=0, max_batch=Bl, max_seq=max_seq, max_prefill_tokens=Bl * S_PREFILL)

@@ -147,9 +147,8 @@ int vcla_bench_decode_gemm(vcla_ctx* ctx, int which, int B, int reps, float* avg
  * 8 resid+rmsnorm, 9 silu*mul, 10/11 logits+argmax, 12 advance, 13 embed.  vcla_trace_read synchronises and clears. */
 int vcla_trace_enable(vcla_ctx* ctx, int max_events);
 int vcla_trace_read(vcla_ctx* ctx, uint64_t* dst_host, int max_events, int* n_events);
-/* launch mode of subsequently enqueued kernels (process-wide): 0 = plain stream order, 1 = programmatic dependent launch
- * (griddepcontrol), 2 = PDL + release/acquire dependency counters inside the decode step */
-void vcla_set_pdl(int mode);
+/* enable/disable programmatic dependent launch for subsequently enqueued kernels (process-wide) */
+void vcla_set_pdl(int on);
 
 #ifdef __cplusplus
 }

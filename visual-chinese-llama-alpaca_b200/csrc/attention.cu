@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
   TraceScope trace(4);
 
   pdl_launch_dependents();
-  dep_wait_block(c.dep);
+  pdl_wait();
   trace.dep();
 
   const int L = c.seq_len[b];          // tokens already cached; the new token gets index L
@@ -370,7 +370,6 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
   }
   if (c.kv_splits == 1) {
     if (tid < HD) c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(O / Lsum);
-    dep_signal_block(c.dep);
     trace.done();
     return;
   }
@@ -385,7 +384,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
     s_last = (old == c.kv_splits - 1);
   }
   __syncthreads();
-  if (!s_last) { dep_signal_block(c.dep); trace.done(); return; }
+  if (!s_last) { trace.done(); return; }
   __threadfence();
   if (tid < HD) {
     const float* base = c.scratch + ((size_t)b * c.H + h) * c.kv_splits * (HD + 2);
@@ -401,7 +400,6 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
     c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(Og / Lg);
   }
   if (tid == 0) c.counters[b * c.H + h] = 0;  // ready for the next step / graph replay
-  dep_signal_block(c.dep);
   trace.done();
 }
 
@@ -411,10 +409,9 @@ VCLA_DEFINE_TRACE_SETTER(trace_set_attention)
 const float* rope_cos_table();
 const float* rope_sin_table();
 
-int attention_decode(DecodeAttnCall c, DepLink* link, cudaStream_t st) {
+int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   if (c.HD != 128) { set_error("attention_decode: head dim %d unsupported (128)", c.HD); return -1; }
   if (rope_cos_table() == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
-  if (link) c.dep = link->take((unsigned int)(c.kv_splits * c.H * c.B));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(kDecWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute attr[1];

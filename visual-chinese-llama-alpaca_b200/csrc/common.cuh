@@ -8,8 +8,6 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#include "kernels.h"
-
 namespace vcla {
 
 typedef __nv_bfloat16 bf16;
@@ -178,44 +176,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-__device__ __forceinline__ void pdl_wait();
-// ------------------------------------------------------------------------------------------------
-// Software dependencies inside the decode step.  A kernel boundary resolved by griddepcontrol.wait costs 4-8 us (grid
-// drain + memory flush, measured: profiles/r1_decode_step_trace_pdl_griddep.json).  Kernels of the decode step are
-// launched with PDL (resident before their inputs exist) and order themselves through release/acquire counters instead:
-// every CTA of kernel i does `red.release.gpu counters[i] += 1` after its outputs are written; kernel i+1 spins until
-// counters[i] == number of CTAs of kernel i.  counters == nullptr selects the hardware path (prefill, tests).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dep_wait_thread(const DepSync& d) {   // executed by ONE thread, follow with a barrier
-  if (d.counters == nullptr || d.wait_idx < 0) { pdl_wait(); return; }
-  const unsigned int expected = (*d.epoch + 1u) * d.wait_ctas;
-  const unsigned int* p = d.counters + d.wait_idx;
-  unsigned int v;
-  long long t0 = 0;
-  while (true) {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    if ((int)(v - expected) >= 0) break;
-    if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > 4000000000LL) {
-      printf("vcla: dependency counter %d stuck at %u of %u (block %d,%d,%d)\n", d.wait_idx, v, expected, blockIdx.x, blockIdx.y, blockIdx.z);
-      __trap();
-    }
-    __nanosleep(32);
-  }
-}
-__device__ __forceinline__ void dep_wait_block(const DepSync& d) {    // whole CTA
-  if (d.counters == nullptr || d.wait_idx < 0) { pdl_wait(); return; }
-  if (threadIdx.x == 0) dep_wait_thread(d);
-  __syncthreads();
-}
-__device__ __forceinline__ void dep_signal_block(const DepSync& d) {  // whole CTA, after its last global write
-  if (d.counters == nullptr || d.signal_idx < 0) return;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(d.counters + d.signal_idx) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // Optional timeline trace (debug / profiles): CTA (0,0,0) thread 0 of every kernel records globaltimer at entry, after

@@ -197,11 +197,10 @@ int embed_tokens(const int64_t* ids, int B, int T, int S, int D, const bf16* tab
   VCLA_LAUNCH(embed_tokens_kernel, dim3(T, B), dim3(128), 0, st, ids, T, S, D, table, vocab, mode, nq, dst);
   return 0;
 }
-__global__ void embed_tokens_i32_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ dst,
-                                        const DepSync dep) {
+__global__ void embed_tokens_i32_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ dst) {
   TraceScope trace(13);
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own dependency wait
-  dep_wait_block(dep);       // first kernel of the decode step: hardware dependency on everything before
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
   trace.dep();
   const int b = blockIdx.x;
   int id = ids[b];
@@ -214,11 +213,9 @@ __global__ void embed_tokens_i32_kernel(const int32_t* __restrict__ ids, int D, 
     *reinterpret_cast<float4*>(d + i) = make_float4(a.x, a.y, bb.x, bb.y);
     *reinterpret_cast<float4*>(d + i + 4) = make_float4(c.x, c.y, e.x, e.y);
   }
-  dep_signal_block(dep);
 }
-int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* dst, DepLink* link, cudaStream_t st) {
-  DepSync dep = link ? link->take((unsigned int)B) : DepSync();
-  VCLA_LAUNCH(embed_tokens_i32_kernel, dim3(B), dim3(256), 0, st, ids, D, table, vocab, dst, dep);
+int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* dst, cudaStream_t st) {
+  VCLA_LAUNCH(embed_tokens_i32_kernel, dim3(B), dim3(256), 0, st, ids, D, table, vocab, dst);
   return 0;
 }
 
@@ -345,14 +342,14 @@ int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv
 constexpr int kNormCluster = 8;
 __global__ void __cluster_dims__(kNormCluster, 1, 1) __launch_bounds__(128)
 dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows, float* __restrict__ resid, int D,
-                      const float* __restrict__ w, float eps, bf16* __restrict__ xn, const DepSync dep) {
+                      const float* __restrict__ w, float eps, bf16* __restrict__ xn) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[32];
   __shared__ float s_part;
   TraceScope trace(8);
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own dependency wait
-  dep_wait_block(dep);
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
   trace.dep();
   const int b = blockIdx.y;
   const int chunk = D / kNormCluster;
@@ -391,50 +388,44 @@ dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows
     *reinterpret_cast<uint2*>(xn + (size_t)b * D + col) =
         make_uint2(pack_bf16x2(v.x * rstd * wv.x, v.y * rstd * wv.y), pack_bf16x2(v.z * rstd * wv.z, v.w * rstd * wv.w));
   }
-  dep_signal_block(dep);
 }
-int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, int B, int D, const float* w, float eps, bf16* xn, DepLink* link, cudaStream_t st) {
+int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, int B, int D, const float* w, float eps, bf16* xn, cudaStream_t st) {
   if (D % (kNormCluster * 4) != 0 || D / kNormCluster > 128 * 4 * 4) { set_error("dec_resid_norm: unsupported D %d", D); return -1; }
-  DepSync dep = link ? link->take((unsigned int)(kNormCluster * B)) : DepSync();
-  VCLA_LAUNCH(dec_resid_norm_kernel, dim3(kNormCluster, B), dim3(128), 0, st, partial, splits, ws_rows, resid, D, w, eps, xn, dep);
+  VCLA_LAUNCH(dec_resid_norm_kernel, dim3(kNormCluster, B), dim3(128), 0, st, partial, splits, ws_rows, resid, D, w, eps, xn);
   return 0;
 }
 
-__global__ void dec_silu_mul_kernel(const float* __restrict__ partial, int splits, int ws_rows, int F, bf16* __restrict__ h, const DepSync dep) {
+__global__ void dec_silu_mul_kernel(const float* __restrict__ partial, int splits, int ws_rows, int F, bf16* __restrict__ h) {
   TraceScope trace(9);
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own dependency wait
-  dep_wait_block(dep);
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
   trace.dep();
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < F) {
-    const int gi = (j >> 5) * 64 + (j & 31);
-    float g = 0.f, u = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float* row = partial + ((size_t)s * ws_rows + b) * (size_t)(2 * F);
-      g += __ldcg(row + gi);
-      u += __ldcg(row + gi + 32);
-    }
-    h[(size_t)b * F + j] = __float2bfloat16(g / (1.f + __expf(-g)) * u);
+  if (j >= F) return;
+  const int gi = (j >> 5) * 64 + (j & 31);
+  float g = 0.f, u = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* row = partial + ((size_t)s * ws_rows + b) * (size_t)(2 * F);
+    g += row[gi];
+    u += row[gi + 32];
   }
-  dep_signal_block(dep);
+  h[(size_t)b * F + j] = __float2bfloat16(g / (1.f + __expf(-g)) * u);
 }
-int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, DepLink* link, cudaStream_t st) {
-  const int gx = (F + 255) / 256;
-  DepSync dep = link ? link->take((unsigned int)(gx * B)) : DepSync();
-  VCLA_LAUNCH(dec_silu_mul_kernel, dim3(gx, B), dim3(256), 0, st, partial, splits, ws_rows, F, h, dep);
+int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st) {
+  VCLA_LAUNCH(dec_silu_mul_kernel, dim3((F + 255) / 256, B), dim3(256), 0, st, partial, splits, ws_rows, F, h);
   return 0;
 }
 
 // logits + argmax: stage 1 per (vocab chunk, b) -> candidate ; stage 2 per b
 constexpr int kArgChunks = 32;
 __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits, int ws_rows, int ldp, int V, float* __restrict__ logits,
-                                  int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx, const DepSync dep) {
+                                  int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
   __shared__ float sv[32];
   __shared__ int si[32];
   TraceScope trace(10);
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own dependency wait
-  dep_wait_block(dep);
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
   trace.dep();
   const int b = blockIdx.y, ch = blockIdx.x;
   const int per = (V + kArgChunks - 1) / kArgChunks;
@@ -443,7 +434,7 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
   int bi = 0x7fffffff;
   for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
     float x = 0.f;
-    for (int s = 0; s < splits; ++s) x += __ldcg(partial + ((size_t)s * ws_rows + b) * (size_t)ldp + v);
+    for (int s = 0; s < splits; ++s) x += partial[((size_t)s * ws_rows + b) * (size_t)ldp + v];
     if (logits) logits[(size_t)b * ld_logits + v] = x;
     if (x > best) { best = x; bi = v; }   // strided order: smaller index kept on ties via the reduction below
   }
@@ -467,23 +458,21 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
     }
     if (lane == 0) { cand_val[b * kArgChunks + ch] = best; cand_idx[b * kArgChunks + ch] = bi; }
   }
-  dep_signal_block(dep);
 }
-__global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok, const DepSync dep) {
+__global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok) {
   TraceScope trace(11);
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own dependency wait
-  dep_wait_block(dep);
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
   trace.dep();
   const int b = blockIdx.x, lane = threadIdx.x;
-  float best = __ldcg(cand_val + b * kArgChunks + lane);
-  int bi = __ldcg(cand_idx + b * kArgChunks + lane);
+  float best = cand_val[b * kArgChunks + lane];
+  int bi = cand_idx[b * kArgChunks + lane];
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, best, o);
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
   if (lane == 0) tok[b] = bi;
-  dep_signal_block(dep);
 }
 static float* g_cand_val = nullptr;
 static int* g_cand_idx = nullptr;
@@ -496,31 +485,23 @@ int argmax_scratch_init(int max_batch) {
   g_cand_cap = max_batch;
   return 0;
 }
-int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok, DepLink* link, cudaStream_t st) {
+int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok, cudaStream_t st) {
   if (g_cand_cap < B) { set_error("argmax scratch too small (%d < %d)", g_cand_cap, B); return -1; }
-  DepSync d1 = link ? link->take((unsigned int)(kArgChunks * B)) : DepSync();
-  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx, d1);
-  DepSync d2 = link ? link->take((unsigned int)B) : DepSync();
-  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok, d2);
+  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx);
+  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok);
   return 0;
 }
 
-__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by, const DepSync dep, unsigned int* epoch_rw) {
+__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by) {
   TraceScope trace(12);
-  pdl_launch_dependents();   // dependents may become resident early; they block in their own dependency wait
-  dep_wait_block(dep);
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
   trace.dep();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) seq_len[b] += by;
-  // last kernel of a decode step: everything before it has completed (transitively), so the step number may advance
-  if (epoch_rw != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *epoch_rw += 1u;
 }
-int advance_seq(int32_t* seq_len, int B, int by, DepLink* link, cudaStream_t st) {
-  const int gx = (B + 63) / 64;
-  if (link && gx != 1) { set_error("advance_seq: decode batch must fit one CTA"); return -1; }
-  DepSync dep = link ? link->take((unsigned int)gx) : DepSync();
-  unsigned int* ep = link ? link->epoch : nullptr;
-  VCLA_LAUNCH(advance_seq_kernel, dim3(gx), dim3(64), 0, st, seq_len, B, by, dep, ep);
+int advance_seq(int32_t* seq_len, int B, int by, cudaStream_t st) {
+  VCLA_LAUNCH(advance_seq_kernel, dim3((B + 63) / 64), dim3(64), 0, st, seq_len, B, by);
   return 0;
 }
 

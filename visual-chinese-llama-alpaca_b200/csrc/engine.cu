@@ -106,7 +106,6 @@ struct vcla_ctx {
   float *ws_qkv = nullptr, *ws_o = nullptr, *ws_gu = nullptr, *ws_d = nullptr, *ws_lm = nullptr;
   float* attn_scratch = nullptr; int32_t* attn_counters = nullptr;
   int32_t* d_tok = nullptr;
-  unsigned int *dep_counters = nullptr, *dep_epoch = nullptr;   // software dependency chain of the decode step
   int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
   // graphs
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -286,8 +285,6 @@ void layout_activations(vcla_ctx* c) {
   c->attn_scratch = a_alloc<float>(c, (size_t)Bp * g.t_heads * c->kv_splits * (128 + 2));
   c->attn_counters = a_alloc<int32_t>(c, (size_t)Bp * g.t_heads);
   c->d_tok = a_alloc<int32_t>(c, Bp);
-  c->dep_counters = a_alloc<unsigned int>(c, kMaxDepCounters);
-  c->dep_epoch = a_alloc<unsigned int>(c, 16);
   c->page_table = a_alloc<int32_t>(c, (size_t)g.max_batch * c->pages_per_seq);
   c->seq_len = a_alloc<int32_t>(c, g.max_batch);
   c->img_row_default = a_alloc<int32_t>(c, g.max_batch);
@@ -319,7 +316,7 @@ extern "C" {
 
 const char* vcla_last_error(void) { return get_error(); }
 const char* vcla_version(void) { return "vcla-b200 0.1 (sm_100a, tcgen05/TMA)"; }
-void vcla_set_pdl(int mode) { set_pdl(mode != 0); set_dep_counters(mode >= 2); }
+void vcla_set_pdl(int on) { set_pdl(on != 0); }
 
 int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   if (!cfg || !out) { set_error("vcla_create: null argument"); return -1; }
@@ -585,19 +582,19 @@ int vcla_vision_encode(vcla_ctx* c, const void* pixels, int pixel_dtype, int B, 
 // -------------------------------------------------------------------------------------------------
 // prefill
 // -------------------------------------------------------------------------------------------------
-static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X, int B, int splits, float* ws, cudaStream_t st, DepLink* link = nullptr) {
+static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X, int B, int splits, float* ws, cudaStream_t st) {
   GemmCall g; g.A = W; g.B = X; g.M = n_out; g.N = B; g.K = K; g.lda = K; g.ldb = K; g.mode = GEMM_PARTIAL_F32; g.out = ws; g.ldo = n_out;
-  g.splits = splits; g.ws_rows = B; g.weights_are_A = 1; g.link = link;
+  g.splits = splits; g.ws_rows = B; g.weights_are_A = 1;
   count(c); return gemm_tc(g, st);
 }
 
 static int lm_head_last(vcla_ctx* c, int B, float* logits_dev, int32_t* tok_dev, cudaStream_t st) {
   // d_resid[B, T] holds the hidden state of the positions to score
   const vcla_config& g = c->cfg;
-  count(c); if (dec_resid_norm(nullptr, 0, B, c->d_resid, B, g.t_hidden, c->final_norm, g.t_eps, c->d_xn, nullptr, st)) return -1;
+  count(c); if (dec_resid_norm(nullptr, 0, B, c->d_resid, B, g.t_hidden, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, g.t_hidden, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
   count(c, 2);
-  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, nullptr, st);
+  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, st);
 }
 
 int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, float* logits_all,
@@ -640,7 +637,7 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
   }
   count(c); if (gather_last_rows(c->resid, B, S, TH, c->d_resid, st)) return -1;
   if (lm_head_last(c, B, last_logits, next_tok, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, S, nullptr, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, S, st)) return -1;
   return 0;
 }
 
@@ -650,31 +647,27 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
 static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
   const vcla_config& g = c->cfg;
   const int TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
-  // kernel-to-kernel ordering inside the step: release/acquire counters (dep mode 2) or griddepcontrol / stream order
-  DepLink chain; chain.counters = c->dep_counters; chain.epoch = c->dep_epoch;
-  DepLink* link = dep_counters_enabled() ? &chain : nullptr;
-  count(c); if (embed_tokens_i32(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, link, st)) return -1;
+  count(c); if (embed_tokens_i32(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, st)) return -1;
   const float scale = 1.0f / sqrtf(128.f);
   for (int i = 0; i < g.t_layers; ++i) {
     const TextLayer& L = c->tl[i];
     // residual += previous layer's down-projection partials ; xn = rmsnorm(residual)
-    count(c); if (dec_resid_norm(i == 0 ? nullptr : c->ws_d, c->sp_d, B, c->d_resid, B, TH, L.ln1, g.t_eps, c->d_xn, link, st)) return -1;
-    if (swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st, link)) return -1;
+    count(c); if (dec_resid_norm(i == 0 ? nullptr : c->ws_d, c->sp_d, B, c->d_resid, B, TH, L.ln1, g.t_eps, c->d_xn, st)) return -1;
+    if (swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st)) return -1;
     DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
     a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
     a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.kv_splits = c->kv_splits; a.scale = scale; a.rope_theta = g.rope_theta;
-    count(c); if (attention_decode(a, link, st)) return -1;
-    if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st, link)) return -1;
-    count(c); if (dec_resid_norm(c->ws_o, c->sp_o, B, c->d_resid, B, TH, L.ln2, g.t_eps, c->d_xn, link, st)) return -1;
-    if (swap_gemm(c, L.wgu, 2 * F, TH, c->d_xn, B, c->sp_gu, c->ws_gu, st, link)) return -1;
-    count(c); if (dec_silu_mul(c->ws_gu, c->sp_gu, B, B, F, c->d_h, link, st)) return -1;
-    if (swap_gemm(c, L.wd, TH, F, c->d_h, B, c->sp_d, c->ws_d, st, link)) return -1;
+    count(c); if (attention_decode(a, st)) return -1;
+    if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st)) return -1;
+    count(c); if (dec_resid_norm(c->ws_o, c->sp_o, B, c->d_resid, B, TH, L.ln2, g.t_eps, c->d_xn, st)) return -1;
+    if (swap_gemm(c, L.wgu, 2 * F, TH, c->d_xn, B, c->sp_gu, c->ws_gu, st)) return -1;
+    count(c); if (dec_silu_mul(c->ws_gu, c->sp_gu, B, B, F, c->d_h, st)) return -1;
+    if (swap_gemm(c, L.wd, TH, F, c->d_h, B, c->sp_d, c->ws_d, st)) return -1;
   }
-  count(c); if (dec_resid_norm(c->ws_d, c->sp_d, B, c->d_resid, B, TH, c->final_norm, g.t_eps, c->d_xn, link, st)) return -1;
-  if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st, link)) return -1;
-  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, link, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, 1, link, st)) return -1;
-  if (link && chain.next_idx > kMaxDepCounters) { set_error("decode: dependency chain too long (%d)", chain.next_idx); return -1; }
+  count(c); if (dec_resid_norm(c->ws_d, c->sp_d, B, c->d_resid, B, TH, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
+  if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
+  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, 1, st)) return -1;
   return 0;
 }
 

@@ -47,9 +47,6 @@ int num_sms() {
 static bool g_pdl = false;
 bool pdl_enabled() { return g_pdl; }
 void set_pdl(bool on) { g_pdl = on; }
-static bool g_depc = false;
-bool dep_counters_enabled() { return g_depc; }
-void set_dep_counters(bool on) { g_depc = on; }
 
 // ------------------------------------------------------------------------------------------------
 // kernel
@@ -66,7 +63,6 @@ struct GemmParams {
   int rows_per_group, group_stride, row_offset;
   int ws_rows;
   uint64_t policy_a, policy_b;
-  DepSync dep;
 };
 
 constexpr int kBlockM = 128;
@@ -158,8 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const CUtensorMap* act_map = SWAP ? &tmB : &tmA;
       const uint64_t act_policy = SWAP ? p.policy_b : p.policy_a;
       auto flush_pending = [&]() {
-        dep_wait_thread(p.dep);          // hardware grid dependency, or the decode step's release/acquire counter
-        fence_proxy_async_global();      // the activation operand was written through the generic proxy, TMA reads it through the async proxy
+        pdl_wait();
         trace.dep();
         for (int i = 0; i < npend; ++i) tma_load_2d(pend_dst[i], act_map, pend_c0[i], pend_c1[i], pend_bar[i], act_policy);
         npend = 0;
@@ -232,9 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue warps =====================
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
-    // hardware path: outputs / residual reads are ordered after the previous grid.  Counter path: the first global
-    // access of this role is causally after the producer's acquire (mbarrier chain: TMA -> MMA -> tcgen05.commit).
-    if (p.dep.counters == nullptr || p.dep.wait_idx < 0) pdl_wait();
+    pdl_wait();                            // outputs / residual reads are ordered after the previous grid
     int acc = 0;
     uint32_t accphase = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -379,7 +372,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  dep_signal_block(p.dep);               // all epilogue stores of this CTA are done
   trace.done();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
@@ -456,7 +448,6 @@ static int launch(const GemmCall& c, GemmParams p, cudaStream_t st) {
   p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int slots = num_sms() * (SWAP ? 2 : 1);
   const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-  if (c.link) p.dep = c.link->take((unsigned int)grid);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);

@@ -14,8 +14,6 @@ const char* get_error();
 int num_sms();
 bool pdl_enabled();
 void set_pdl(bool on);
-bool dep_counters_enabled();
-void set_dep_counters(bool on);
 
 #define VCLA_CUDA_OK(expr)                                                                   \
   do {                                                                                       \
@@ -26,36 +24,6 @@ void set_dep_counters(bool on);
       return -1;                                                                             \
     }                                                                                        \
   } while (0)
-
-// ------------------------------------------------------------------------------------------
-// software dependency chain of the decode step (see common.cuh: DepSync)
-// ------------------------------------------------------------------------------------------
-struct DepSync {
-  unsigned int* counters = nullptr;       // nullptr: hardware path (griddepcontrol.wait)
-  const unsigned int* epoch = nullptr;    // decode-step number; counters grow monotonically, expected = (epoch+1) * wait_ctas
-  int wait_idx = -1;                      // -1: first kernel of the step (falls back to griddepcontrol.wait)
-  unsigned int wait_ctas = 0;
-  int signal_idx = -1;
-};
-struct DepLink {             // host-side builder: each launcher consumes the previous kernel's CTA count and publishes its own
-  unsigned int* counters = nullptr;
-  unsigned int* epoch = nullptr;
-  int next_idx = 0;
-  unsigned int prev_ctas = 0;
-  DepSync take(unsigned int my_ctas) {
-    DepSync a;
-    if (!counters) return a;
-    a.counters = counters;
-    a.epoch = epoch;
-    a.wait_idx = next_idx - 1;
-    a.wait_ctas = prev_ctas;
-    a.signal_idx = next_idx;
-    ++next_idx;
-    prev_ctas = my_ctas;
-    return a;
-  }
-};
-constexpr int kMaxDepCounters = 1024;
 
 // ------------------------------------------------------------------------------------------
 // tcgen05 GEMM:  D[M,N] = A[M,K] * B[N,K]^T   (both operands K-major bf16, fp32 accumulate in TMEM)
@@ -90,7 +58,6 @@ struct GemmCall {
   int ws_rows = 0;           // padded batch rows in the partial workspace
   int weights_are_A = 0;     // cache-policy hint: A is the streamed-once operand (decode)
   int bn = 0;                // tile N override (0 = auto)
-  DepLink* link = nullptr;   // decode step: software dependency chain
 };
 int gemm_tc(const GemmCall& c, cudaStream_t st);
 // correctness reference for the tests only (CUDA-core, one thread per output)
@@ -126,9 +93,8 @@ struct DecodeAttnCall {
   int32_t* counters = nullptr;         // [B][H]
   int B = 0, H = 0, HD = 0, kv_splits = 1;
   float scale = 1.f, rope_theta = 10000.f;
-  DepSync dep;
 };
-int attention_decode(DecodeAttnCall c, DepLink* link, cudaStream_t st);
+int attention_decode(const DecodeAttnCall& c, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // normalisation / elementwise / data movement
@@ -147,7 +113,7 @@ int broadcast_rows(const float* src, int rows, int D, int B, float* dst_f32, bf1
 //   mode 1: image at head: t<2 -> t ; t>=2 -> t + nq
 int embed_tokens(const int64_t* ids, int B, int T, int S, int D, const bf16* table, int vocab, int mode, int nq,
                  float* dst, cudaStream_t st);
-int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* dst, DepLink* link, cudaStream_t st);
+int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* dst, cudaStream_t st);
 // copy the projected image rows (B, nq, D) fp32 into the residual stream at per-sample row offsets
 int scatter_image_rows(const float* img, int B, int nq, int D, const int32_t* row_start, int S, float* dst, cudaStream_t st);
 // prefill: RoPE q,k in place in the fused qkv buffer [B*S, 3T] and append k,v to the paged cache
@@ -158,13 +124,13 @@ int gather_last_rows(const float* hidden, int B, int S, int D, float* dst, cudaS
 // decode consumers of split-K partials
 // resid[b,:] += sum_s partial[s][b][:]  (partial may be null) ; xn = rmsnorm(resid) -> bf16
 int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, int B, int D, const float* w, float eps,
-                   bf16* xn, DepLink* link, cudaStream_t st);
+                   bf16* xn, cudaStream_t st);
 // h[b, j] = silu(sum_s p[s][b][g(j)]) * (sum_s p[s][b][u(j)])  with the [32 gate | 32 up] interleave
-int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, DepLink* link, cudaStream_t st);
+int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st);
 // logits[b, :] = sum_s partial[s][b][:V] ; tok[b] = argmax (first max wins, like torch.argmax)
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits,
-                      int32_t* tok, DepLink* link, cudaStream_t st);
-int advance_seq(int32_t* seq_len, int B, int by, DepLink* link, cudaStream_t st);
+                      int32_t* tok, cudaStream_t st);
+int advance_seq(int32_t* seq_len, int B, int by, cudaStream_t st);
 int rope_init(int max_pos, int head_dim, float theta);
 int argmax_scratch_init(int max_batch);
 const float* rope_cos_table();

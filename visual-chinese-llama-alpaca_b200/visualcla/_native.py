@@ -75,7 +75,7 @@ def load():
         fn.restype = res
         fn.argtypes = args
     if os.environ.get("VCLA_PDL", "") not in ("", "0"):
-        lib.vcla_set_pdl(int(os.environ["VCLA_PDL"]))   # 1: PDL, 2: PDL + dependency counters in the decode step
+        lib.vcla_set_pdl(1)        # programmatic dependent launch for every kernel enqueued afterwards
     _lib = lib
     return lib
 
