@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=8)
     ap.add_argument("--new-tokens", type=int, default=N_NEW)
+    ap.add_argument("--prompt-tokens", type=int, default=T_TEXT, help="text tokens per prompt (64 = configs[1]; 128 = configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("VCLA_PDL", "1")))
     return ap.parse_args()
@@ -108,12 +109,12 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_inputs(B, seed=1234):
+def synth_inputs(B, seed=1234, T=T_TEXT):
     """randn pixels (CLIP-normalised scale), ids = [BOS, <img>, </img>, uniform random...]."""
     import torch
     g = torch.Generator().manual_seed(seed)
     px = torch.randn(B, 3, 224, 224, generator=g).half()
-    ids = torch.randint(3, 49954, (B, T_TEXT), generator=g)
+    ids = torch.randint(3, 49954, (B, T), generator=g)
     ids[:, 0], ids[:, 1], ids[:, 2] = 1, 49954, 49955
     return px, ids
 
@@ -216,11 +217,12 @@ def run_native(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     _native.load().vcla_set_pdl(1 if args.pdl else 0)
     Bl, B, n_new = args.batch_per_gpu, args.batch_per_gpu * world, args.new_tokens
+    T_TEXT, S_PREFILL = args.prompt_tokens, args.prompt_tokens + NQ     # shadow the module defaults (configs[1]) when overridden
     max_seq = S_PREFILL + n_new + 1
     model = visualcla.VisualCLAModel.from_synthetic("7b", seed=0, max_batch=Bl, max_seq=max_seq, max_prefill_tokens=Bl * S_PREFILL)
     model.image_at_head = True
     eng = model._engine
-    px_h, ids_h = synth_inputs(B)
+    px_h, ids_h = synth_inputs(B, T=T_TEXT)
     px_h, ids_h = px_h.pin_memory(), ids_h.pin_memory()
     px_d, ids_d = px_h.cuda(non_blocking=True), ids_h.cuda(non_blocking=True)
     torch.cuda.synchronize()
@@ -277,7 +279,7 @@ def run_native(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (randn 224x224 pixels, uniform random token ids, hash-normal weights of the VisualCLA-7B architecture)",
-            "config": {"workload": f"configs[1]: batch {Bl} per GPU x {world} GPU, 224x224 images, {T_TEXT}-token prompts (S={S_PREFILL} with 64 image tokens), "
+            "config": {"workload": f"configs[{1 if (Bl, T_TEXT) == (8, 64) else 2 if (Bl, T_TEXT) == (32, 128) else '*'}]: batch {Bl} per GPU x {world} GPU, 224x224 images, {T_TEXT}-token prompts (S={S_PREFILL} with 64 image tokens), "
                                    f"{n_new}-token greedy decode, EOS disabled", "global_batch": B, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: every decode step streams 13.4 GB of weights (>> 126 MB L2)", "pdl": bool(args.pdl)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(px_h.numel() * 2 + ids_h.numel() * 8),

@@ -209,7 +209,7 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
 // =================================================================================================
 // decode (hd = 128): grid (kv_splits, H, B), 128 threads
 // =================================================================================================
-constexpr int kDecWarps = 4;   // 128 threads: 7 CTAs/SM keep all B*H*splits CTAs resident in one wave (8 warps: 2.3 waves, 60 % slower)
+constexpr int kDecWarps = 8;   // 256 threads = 32 cached tokens in flight per CTA iteration; the host keeps B*H*kv_splits within one wave (3 CTAs/SM)
 __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
                                                                      const float* __restrict__ rope_sin) {
   constexpr int HD = 128;

@@ -282,7 +282,7 @@ void layout_activations(vcla_ctx* c) {
   c->ws_gu = a_alloc<float>(c, (size_t)c->sp_gu * Bp * 2 * F);
   c->ws_d = a_alloc<float>(c, (size_t)c->sp_d * Bp * T);
   c->ws_lm = a_alloc<float>(c, (size_t)c->sp_lm * Bp * g.t_vocab);
-  c->attn_scratch = a_alloc<float>(c, (size_t)Bp * g.t_heads * c->kv_splits * (128 + 2));
+  c->attn_scratch = a_alloc<float>(c, (size_t)Bp * g.t_heads * 8 * (128 + 2));   // up to 8 KV splits
   c->attn_counters = a_alloc<int32_t>(c, (size_t)Bp * g.t_heads);
   c->d_tok = a_alloc<int32_t>(c, Bp);
   c->page_table = a_alloc<int32_t>(c, (size_t)g.max_batch * c->pages_per_seq);
@@ -350,7 +350,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   c->sp_gu = pick_splits(2 * g.t_ffn, g.t_hidden);
   c->sp_d = pick_splits(g.t_hidden, g.t_ffn);
   c->sp_lm = pick_splits(g.t_vocab, g.t_hidden);
-  c->kv_splits = g.max_seq >= 1024 ? 8 : (g.max_seq >= 256 ? 4 : 1);
+  c->kv_splits = g.max_seq >= 1536 ? 4 : (g.max_seq >= 768 ? 2 : 1);   // context-driven minimum; raised per call for small batches
 
   if (gemm_init()) { delete c; return -1; }
   // sizing passes
@@ -656,7 +656,9 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
     if (swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st)) return -1;
     DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
     a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
-    a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.kv_splits = c->kv_splits; a.scale = scale; a.rope_theta = g.rope_theta;
+    a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta;
+    // one wave of 256-thread CTAs (3 per SM): enough CTAs to cover the SMs, never more than fit at once
+    { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
     count(c); if (attention_decode(a, st)) return -1;
     if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st)) return -1;
     count(c); if (dec_resid_norm(c->ws_o, c->sp_o, B, c->d_resid, B, TH, L.ln2, g.t_eps, c->d_xn, st)) return -1;
