@@ -209,8 +209,9 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
 // =================================================================================================
 // decode (hd = 128): grid (kv_splits, H, B), 128 threads
 // =================================================================================================
+constexpr int kMaxPagesPerSplit = 128;   // pages one CTA may touch (host checks max_seq / page_tokens / kv_splits)
 constexpr int kDecWarps = 8;   // 256 threads = 32 cached tokens in flight per CTA iteration; the host keeps B*H*kv_splits within one wave (3 CTAs/SM)
-__global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+__global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
                                                                      const float* __restrict__ rope_sin) {
   constexpr int HD = 128;
   __shared__ float s_q[HD];
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
   __shared__ float s_v[HD];
   __shared__ float s_acc[kDecWarps][HD];
   __shared__ float s_m[kDecWarps], s_l[kDecWarps];
+  __shared__ int s_pages[kMaxPagesPerSplit];
   __shared__ int s_last;
 
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -237,6 +239,13 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
   const int t_end = min(n, t_begin + chunk);
   const bool owns_new = (t_begin <= L) && (L < t_end);
 
+  // ---- stage this CTA's page ids (independent of everything below: overlaps the partial-sum loads)
+  {
+    const int p0 = t_begin / c.page_tokens;
+    const int p1 = (min(t_end, L) + c.page_tokens - 1) / c.page_tokens;
+    for (int i = tid; i < p1 - p0 && i < kMaxPagesPerSplit; i += blockDim.x)
+      s_pages[i] = __ldg(c.page_table + (size_t)b * c.pages_per_seq + p0 + i);
+  }
   // ---- reduce the split-K partials of this head's q (and k, v if this CTA owns the new token); RoPE
   {
     const int d = tid & (HD - 1);
@@ -277,7 +286,10 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
     __syncthreads();
   }
 
-  // ---- attention over cached tokens [t_begin, min(t_end, L)): 8 lanes per token, 16 dims per lane
+  // ---- attention over cached tokens [t_begin, min(t_end, L)): 8 lanes per token, 16 dims per lane.
+  // Page ids of this CTA's token range were staged in smem by the prologue; K/V rows of the NEXT iteration are
+  // requested before the current one is reduced (register double buffer), so one DRAM latency is exposed per CTA
+  // instead of two per iteration.
   const int grp = lane >> 3, sub = lane & 7;
   const uint32_t gmask = 0xffu << (grp * 8);
   float qreg[16];
@@ -288,13 +300,28 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 
   const int c_end = min(t_end, L);
-  __syncwarp();
-  for (int t = t_begin + warp * 4 + grp; t < c_end; t += kDecWarps * 4) {
-    const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + t / c.page_tokens);
+  const int page0 = t_begin / c.page_tokens;
+  auto kv_ptr = [&](int t, int which) {
+    const int page = s_pages[t / c.page_tokens - page0];
     const int slot = t % c.page_tokens;
-    const uint4* kp = reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
-    const uint4* vp = reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
-    uint4 k0 = __ldg(kp), k1 = __ldg(kp + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
+    return reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + which) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
+  };
+  __syncwarp();
+  int t = t_begin + warp * 4 + grp;
+  uint4 k0, k1, v0, v1;
+  if (t < c_end) {
+    const uint4* kp = kv_ptr(t, 0);
+    const uint4* vp = kv_ptr(t, 1);
+    k0 = __ldg(kp); k1 = __ldg(kp + 1); v0 = __ldg(vp); v1 = __ldg(vp + 1);
+  }
+  while (t < c_end) {
+    const int tn = t + kDecWarps * 4;
+    uint4 nk0, nk1, nv0, nv1;
+    if (tn < c_end) {
+      const uint4* kp = kv_ptr(tn, 0);
+      const uint4* vp = kv_ptr(tn, 1);
+      nk0 = __ldg(kp); nk1 = __ldg(kp + 1); nv0 = __ldg(vp); nv1 = __ldg(vp + 1);
+    }
     const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
     const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     float sc = 0.f;
@@ -317,6 +344,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) attn_decode_kernel(const Decod
       acc[2 * i] = acc[2 * i] * cr + p * vf.x;
       acc[2 * i + 1] = acc[2 * i + 1] * cr + p * vf.y;
     }
+    k0 = nk0; k1 = nk1; v0 = nv0; v1 = nv1;
+    t = tn;
   }
   __syncwarp();
   // the new token (from smem), handled by warp 0 group 0 of the owning CTA
@@ -412,6 +441,7 @@ const float* rope_sin_table();
 int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   if (c.HD != 128) { set_error("attention_decode: head dim %d unsupported (128)", c.HD); return -1; }
   if (rope_cos_table() == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
+  if ((c.pages_per_seq + c.kv_splits - 1) / c.kv_splits + 2 > kMaxPagesPerSplit) { set_error("attention_decode: context too long for %d KV splits", c.kv_splits); return -1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(kDecWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -290,19 +290,31 @@ void layout_activations(vcla_ctx* c) {
   c->img_row_default = a_alloc<int32_t>(c, g.max_batch);
 }
 
-// choose split-K factors so every decode GEMM launches ~2 waves of 2-CTA/SM work with >= 8 k-blocks per split
+// Split-K factor of a decode GEMM (row tiles of 128 x `splits` work units on 2 persistent CTAs per SM).  Measured on B200
+// (profiles/r1_decode_step_trace_*.json): a thin last wave is latency-bound (one lone CTA streams ~80 GB/s), and a single
+// wave of one-tile CTAs loses the epilogue/load overlap -> prefer >= ~2 waves with a last wave that is >= 60 % full.
 int pick_splits(int n_out, int K) {
   const int tiles = (n_out + 127) / 128;
   const int kb = (K + 63) / 64;
-  const int target = 2 * 148 * 2;   // ~2 tiles per persistent CTA: the epilogue of tile i overlaps the loads of tile i+1 (1 tile/CTA measured 15 % slower)
-  int s = (target + tiles - 1) / tiles;
-  int max_s = kb / 8; if (max_s < 1) max_s = 1;
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  // make it realisable: every split non-empty with equal kb_per_split
-  int per = (kb + s - 1) / s;
-  s = (kb + per - 1) / per;
-  return s;
+  const double slots = 2.0 * 148;
+  int best = 1;
+  double best_score = 1e9;
+  for (int want = 1; want <= 40; ++want) {
+    if (kb / want < 4 && want > 1) break;               // at least 4 k-blocks per work unit
+    const int per = (kb + want - 1) / want;
+    const int s = (kb + per - 1) / per;                 // realisable: every split non-empty
+    if (s != want) continue;
+    const double w = tiles * (double)s / slots;
+    const double f = w - floor(w);
+    double score;
+    if (w < 1.0) score = (1.0 - w) + 0.15;
+    else if (f < 1e-9) score = 0.0;
+    else if (f >= 0.6) score = (1.0 - f) * 0.3;
+    else score = (0.6 - f) + 0.2;
+    score += 0.01 * s;                                  // fewer partials for the consumers when otherwise equal
+    if (score < best_score) { best_score = score; best = s; }
+  }
+  return best;
 }
 
 int count(vcla_ctx* c, int n = 1) { c->launches += n; return 0; }
