@@ -136,22 +136,24 @@ def _run_vs_oracle(cfg, seed, B, T, n_new, max_seq, logit_tol=LOGIT_TOL, weights
     scale = o_log.abs().max().item()
     err = (d_log.cpu() - o_log).abs().max().item() / scale
     nbad, ndec, ntot = _margin_ok_tokens(d_tok.long(), o_tok, o_log, logit_tol * scale)
-    return m, err, nbad, ndec, ntot, o_tok
+    return m, err, nbad, ndec, ntot, o_tok, o_log
 
 
 def test_mid_config_vs_oracle():
     """ViT/Resampler at real width but few layers, LLaMA at 1024 width: exercises 257-token ViT, 64x321 resampler
     attention, multi-tile GEMMs, multi-page KV cache and 40 decode steps."""
     cfg = O.PathConfig(v_layers=2, r_layers=2, t_hidden=1024, t_heads=8, t_ffn=2752, t_layers=3, t_vocab=5003)
-    m, err, nbad, ndec, ntot, o_tok = _run_vs_oracle(cfg, 5, 3, 70, 40, 256)
+    m, err, nbad, ndec, ntot, o_tok, o_log = _run_vs_oracle(cfg, 5, 3, 70, 40, 256)
     assert err <= LOGIT_TOL, f"teacher-forced logits rel err {err:.3e}"
     assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
     # free-running greedy on the device == oracle tokens wherever decisive (here: compare the prefix up to first diff)
     px, ids = O.make_inputs(cfg, 3, 70, seed=77 + 5)
     out = m.generate(input_ids=ids.cuda(), pixel_values=px.cuda(), do_sample=False, max_new_tokens=40, eos_token_id=None, pad_token_id=0)
     assert out.shape == (3, 40)
-    agree = (out.cpu() == o_tok).float().mean().item()
-    assert agree > 0.5, f"free-running agreement {agree:.2f}"
+    # free-running: every sequence must follow the oracle up to its first mismatch, and that mismatch must be a
+    # non-decisive step (top-1/top-2 margin within the logit tolerance); later steps condition on different prefixes
+    nbad, ndec, ntot = _margin_ok_tokens(out, o_tok, o_log, LOGIT_TOL * o_log.abs().max().item(), free_running=True)
+    assert nbad == 0, f"free-running: {nbad} decisive tokens differ before the first divergence ({ndec}/{ntot} decisive)"
 
 
 def test_batch_invariance_row_for_row():
@@ -217,7 +219,7 @@ def test_config1_7b_logit_parity_gate():
     def dl(m):
         return {k: v.float() for k, v in m.state_dict().items()}
 
-    m, err, nbad, ndec, ntot, _ = _run_vs_oracle(cfg, 0, 1, 32, n_new, 256, weights=dl)
+    m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 0, 1, 32, n_new, 256, weights=dl)
     print(f"[7B parity] teacher-forced logits rel err {err:.3e}; decisive tokens {ndec}/{ntot}, mismatches {nbad}")
     assert err <= LOGIT_TOL
     assert nbad == 0
