@@ -5,6 +5,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -107,6 +108,7 @@ struct vcla_ctx {
   float* attn_scratch = nullptr; int32_t* attn_counters = nullptr;
   int32_t* d_tok = nullptr;
   int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
+  int l2_prefetch_kb = 24;   // decode GEMMs: weight k-blocks per CTA prefetched into L2 during the dependency wait (VCLA_L2_PREFETCH_KB)
   // graphs
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int64_t> graph_launches;
@@ -362,6 +364,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   c->sp_gu = pick_splits(2 * g.t_ffn, g.t_hidden);
   c->sp_d = pick_splits(g.t_hidden, g.t_ffn);
   c->sp_lm = pick_splits(g.t_vocab, g.t_hidden);
+  if (const char* e = getenv("VCLA_L2_PREFETCH_KB")) c->l2_prefetch_kb = atoi(e);
   c->kv_splits = g.max_seq >= 1536 ? 4 : (g.max_seq >= 768 ? 2 : 1);   // context-driven minimum; raised per call for small batches
 
   if (gemm_init()) { delete c; return -1; }
@@ -596,7 +599,7 @@ int vcla_vision_encode(vcla_ctx* c, const void* pixels, int pixel_dtype, int B, 
 // -------------------------------------------------------------------------------------------------
 static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X, int B, int splits, float* ws, cudaStream_t st) {
   GemmCall g; g.A = W; g.B = X; g.M = n_out; g.N = B; g.K = K; g.lda = K; g.ldb = K; g.mode = GEMM_PARTIAL_F32; g.out = ws; g.ldo = n_out;
-  g.splits = splits; g.ws_rows = B; g.weights_are_A = 1;
+  g.splits = splits; g.ws_rows = B; g.weights_are_A = 1; g.l2_prefetch_kb = c->l2_prefetch_kb;
   count(c); return gemm_tc(g, st);
 }
 

@@ -62,6 +62,7 @@ struct GemmParams {
   int rowtab_period;
   int rows_per_group, group_stride, row_offset;
   int ws_rows;
+  int l2_prefetch_kb;
   uint64_t policy_a, policy_b;
 };
 
@@ -182,7 +183,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               pend_dst[npend] = sa; pend_bar[npend] = full_bar(stage); pend_c0[npend] = kb * kBlockK; pend_c1[npend] = m_blk * kBlockM; ++npend;
             }
           }
-          if (!dep_ready && npend == STAGES) flush_pending();
+          if (!dep_ready && npend == STAGES) {
+            // The smem ring is full and the dependency is (probably) still unresolved: HBM would idle while the small
+            // consumer kernel in front of us runs.  Pull this CTA's NEXT weight tiles into the 126 MB L2 so the main loop
+            // streams them from L2 afterwards.
+            if (p.l2_prefetch_kb > 0) {
+              int budget = p.l2_prefetch_kb;
+              int kbn = kb + 1;
+              for (int t2 = t; t2 < p.total_tiles && budget > 0; t2 += gridDim.x) {
+                int m2, n2, k0, k1, s2;
+                tile_coords(t2, m2, n2, k0, k1, s2);
+                for (int kk = (t2 == t ? kbn : k0); kk < k1 && budget > 0; ++kk, --budget) {
+                  if constexpr (SWAP) tma_prefetch_l2_2d(&tmA, kk * kBlockK, m2 * kBlockM);
+                  else tma_prefetch_l2_2d(&tmB, kk * kBlockK, n2 * BN);
+                }
+              }
+            }
+            flush_pending();
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -481,6 +499,7 @@ int gemm_tc(const GemmCall& c, cudaStream_t st) {
   p.rowtab = c.rowtab; p.rowtab_period = c.rowtab_period > 0 ? c.rowtab_period : 1;
   p.rows_per_group = c.rows_per_group; p.group_stride = c.group_stride; p.row_offset = c.row_offset;
   p.ws_rows = c.ws_rows;
+  p.l2_prefetch_kb = c.l2_prefetch_kb;
   p.policy_a = c.weights_are_A ? kEvictFirst : kEvictLast;
   p.policy_b = c.weights_are_A ? kEvictLast : kEvictNormal;
 

@@ -58,6 +58,7 @@ struct GemmCall {
   int ws_rows = 0;           // padded batch rows in the partial workspace
   int weights_are_A = 0;     // cache-policy hint: A is the streamed-once operand (decode)
   int bn = 0;                // tile N override (0 = auto)
+  int l2_prefetch_kb = 0;    // k-blocks of the weight operand each CTA prefetches into L2 while it waits for its dependency
 };
 int gemm_tc(const GemmCall& c, cudaStream_t st);
 // correctness reference for the tests only (CUDA-core, one thread per output)
