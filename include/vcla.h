@@ -118,6 +118,10 @@ int vcla_prefill(vcla_ctx* ctx, const int64_t* ids_dev, int B, int T, int image_
 int vcla_decode_step(vcla_ctx* ctx, const int32_t* tok_in_dev, int B, float* logits_dev, int32_t* tok_out_dev, int use_graph,
                      vcla_stream stream);
 
+/* Tokens chosen so far: row 0 = the prefill's argmax, row s = decode step s.  Copies [n_steps, B] int32 to a DEVICE buffer
+ * (async on `stream`): lets a greedy loop run as pure graph replays with no per-step host or torch work. */
+int vcla_read_history(vcla_ctx* ctx, int32_t* dst_dev, int B, int n_steps, vcla_stream stream);
+
 /* number of this library's kernels launched by the context since the last call with reset != 0 */
 int64_t vcla_kernel_launches(vcla_ctx* ctx, int reset);
 

@@ -28,12 +28,18 @@ class _StubEngine:
     def prefill(self, ids, mode, rows, all_logits=False, last_logits=False):
         self.state = (ids.sum(1) * 7 + (self.vis * 1000).long()) % 1009
         self.pos = 0
-        return None, (self.state % 997).to(torch.int32), None
+        first = (self.state % 997).to(torch.int32)
+        self.hist = [first.clone()]
+        return None, first, None
 
     def decode_step(self, tok_in, tok_out, logits=None, use_graph=True):
         self.calls += 1
         self.pos += 1
         tok_out.copy_(((tok_in.long() * 31 + self.state + self.pos) % 997).to(torch.int32))
+        self.hist.append(tok_out.clone())
+
+    def read_history(self, B, n_steps):
+        return torch.stack(self.hist[:n_steps], 0)
 
 
 class _StubModel:

@@ -467,7 +467,8 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
     if (lane == 0) { cand_val[b * kArgChunks + ch] = best; cand_idx[b * kArgChunks + ch] = bi; }
   }
 }
-__global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok) {
+__global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok,
+                                  int32_t* __restrict__ history, const int32_t* __restrict__ step_idx) {
   TraceScope trace(11);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
@@ -480,7 +481,10 @@ __global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int*
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
-  if (lane == 0) tok[b] = bi;
+  if (lane == 0) {
+    tok[b] = bi;
+    if (history) history[(size_t)(*step_idx) * gridDim.x + b] = bi;   // [step][B] log of every chosen token since the prefill
+  }
 }
 static float* g_cand_val = nullptr;
 static int* g_cand_idx = nullptr;
@@ -493,23 +497,25 @@ int argmax_scratch_init(int max_batch) {
   g_cand_cap = max_batch;
   return 0;
 }
-int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok, cudaStream_t st) {
+int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok,
+                      int32_t* history, const int32_t* step_idx, cudaStream_t st) {
   if (g_cand_cap < B) { set_error("argmax scratch too small (%d < %d)", g_cand_cap, B); return -1; }
   VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx);
-  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok);
+  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok, history, step_idx);
   return 0;
 }
 
-__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by) {
+__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by, int32_t* step_idx) {
   TraceScope trace(12);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
   trace.dep();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) seq_len[b] += by;
+  if (step_idx != nullptr && b == 0) *step_idx += 1;
 }
-int advance_seq(int32_t* seq_len, int B, int by, cudaStream_t st) {
-  VCLA_LAUNCH(advance_seq_kernel, dim3((B + 63) / 64), dim3(64), 0, st, seq_len, B, by);
+int advance_seq(int32_t* seq_len, int B, int by, int32_t* step_idx, cudaStream_t st) {
+  VCLA_LAUNCH(advance_seq_kernel, dim3((B + 63) / 64), dim3(64), 0, st, seq_len, B, by, step_idx);
   return 0;
 }
 

@@ -107,8 +107,11 @@ struct vcla_ctx {
   float *ws_qkv = nullptr, *ws_o = nullptr, *ws_gu = nullptr, *ws_d = nullptr, *ws_lm = nullptr;
   float* attn_scratch = nullptr; int32_t* attn_counters = nullptr;
   int32_t* d_tok = nullptr;
+  int32_t *tok_hist = nullptr, *step_idx = nullptr;   // tokens of every step since the last prefill, appended by the argmax kernel
   int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
-  int l2_prefetch_kb = 24;   // decode GEMMs: weight k-blocks per CTA prefetched into L2 during the dependency wait (VCLA_L2_PREFETCH_KB)
+  int l2_prefetch_kb = 0;    // decode GEMMs: weight k-blocks per CTA prefetched into L2 during the dependency wait (VCLA_L2_PREFETCH_KB).
+                             // Measured harmful on B200 (0/8/16/24/48 -> 3142/3226/3349/3390/3437 us per step: the prefetch traffic delays
+                             // the latency-critical consumer kernel in front of the GEMM), so it is off by default.
   // graphs
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int64_t> graph_launches;
@@ -287,6 +290,8 @@ void layout_activations(vcla_ctx* c) {
   c->attn_scratch = a_alloc<float>(c, (size_t)Bp * g.t_heads * 8 * (128 + 2));   // up to 8 KV splits
   c->attn_counters = a_alloc<int32_t>(c, (size_t)Bp * g.t_heads);
   c->d_tok = a_alloc<int32_t>(c, Bp);
+  c->tok_hist = a_alloc<int32_t>(c, (size_t)(g.max_seq + 2) * Bp);
+  c->step_idx = a_alloc<int32_t>(c, 16);
   c->page_table = a_alloc<int32_t>(c, (size_t)g.max_batch * c->pages_per_seq);
   c->seq_len = a_alloc<int32_t>(c, g.max_batch);
   c->img_row_default = a_alloc<int32_t>(c, g.max_batch);
@@ -522,6 +527,7 @@ int vcla_init_synthetic(vcla_ctx* c, uint32_t seed, vcla_stream stream) {
 int vcla_reset(vcla_ctx* c, vcla_stream stream) {
   VCLA_CUDA_OK(cudaMemsetAsync(c->seq_len, 0, (size_t)c->cfg.max_batch * 4, (cudaStream_t)stream));
   VCLA_CUDA_OK(cudaMemsetAsync(c->attn_counters, 0, (size_t)64 * c->cfg.t_heads * 4, (cudaStream_t)stream));
+  VCLA_CUDA_OK(cudaMemsetAsync(c->step_idx, 0, 4, (cudaStream_t)stream));
   return 0;
 }
 
@@ -609,7 +615,7 @@ static int lm_head_last(vcla_ctx* c, int B, float* logits_dev, int32_t* tok_dev,
   count(c); if (dec_resid_norm(nullptr, 0, B, c->d_resid, B, g.t_hidden, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, g.t_hidden, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
   count(c, 2);
-  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, st);
+  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, c->tok_hist, c->step_idx, st);
 }
 
 int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, float* logits_all,
@@ -652,7 +658,7 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
   }
   count(c); if (gather_last_rows(c->resid, B, S, TH, c->d_resid, st)) return -1;
   if (lm_head_last(c, B, last_logits, next_tok, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, S, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, S, c->step_idx, st)) return -1;
   return 0;
 }
 
@@ -683,8 +689,8 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
   }
   count(c); if (dec_resid_norm(c->ws_d, c->sp_d, B, c->d_resid, B, TH, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
-  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, 1, st)) return -1;
+  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, c->tok_hist, c->step_idx, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, 1, c->step_idx, st)) return -1;
   return 0;
 }
 
@@ -772,6 +778,13 @@ int vcla_bench_decode_gemm(vcla_ctx* c, int which, int B, int reps, float* avg_u
     *weight_bytes = n[which] * 2;
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int vcla_read_history(vcla_ctx* c, int32_t* dst_dev, int B, int n_steps, vcla_stream stream) {
+  // tokens chosen by the prefill (step 0) and every decode step since, as a device [n_steps, B] int32 array
+  if (n_steps < 0 || n_steps > c->cfg.max_seq + 1 || B < 1 || B > 64) { set_error("vcla_read_history: bad arguments"); return -1; }
+  VCLA_CUDA_OK(cudaMemcpyAsync(dst_dev, c->tok_hist, (size_t)n_steps * B * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 

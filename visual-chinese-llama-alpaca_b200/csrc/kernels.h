@@ -130,8 +130,8 @@ int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, 
 int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st);
 // logits[b, :] = sum_s partial[s][b][:V] ; tok[b] = argmax (first max wins, like torch.argmax)
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits,
-                      int32_t* tok, cudaStream_t st);
-int advance_seq(int32_t* seq_len, int B, int by, cudaStream_t st);
+                      int32_t* tok, int32_t* history, const int32_t* step_idx, cudaStream_t st);
+int advance_seq(int32_t* seq_len, int B, int by, int32_t* step_idx, cudaStream_t st);
 int rope_init(int max_pos, int head_dim, float theta);
 int argmax_scratch_init(int max_batch);
 const float* rope_cos_table();

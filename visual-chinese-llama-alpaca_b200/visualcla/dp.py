@@ -67,12 +67,18 @@ def generate_dp(model, input_ids: torch.Tensor, pixel_values: Optional[torch.Ten
         tok[:nloc].copy_(first)
     if phase_hook is not None:
         phase_hook("prefill_done")
-    for step in range(max_new_tokens):
-        if step > 0 and nloc > 0:
+    if world == 1 and step_hook is None:
+        # single GPU: the graph appends every chosen token to a device-side history -> the loop is pure graph replays
+        for step in range(1, max_new_tokens):
             eng.decode_step(tok[:nloc], tok[:nloc], None)
-        out[:, step] = gather_step_tokens(tok[:nloc], B, group)
-        if step_hook is not None:
-            step_hook(step)
+        out.copy_(eng.read_history(nloc, max_new_tokens).t())
+    else:
+        for step in range(max_new_tokens):
+            if step > 0 and nloc > 0:
+                eng.decode_step(tok[:nloc], tok[:nloc], None)
+            out[:, step] = gather_step_tokens(tok[:nloc], B, group)
+            if step_hook is not None:
+                step_hook(step)
     if phase_hook is not None:
         phase_hook("done")
     return out

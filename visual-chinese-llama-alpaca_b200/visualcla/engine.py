@@ -149,6 +149,13 @@ class Engine:
             N.check(self.lib.vcla_decode_step(self._ctx, N.ptr(tok_in), B, N.ptr(logits), N.ptr(tok_out), 1 if use_graph else 0,
                                               self._stream()), "vcla_decode_step")
 
+    def read_history(self, B: int, n_steps: int) -> torch.Tensor:
+        """(n_steps, B) int32 CUDA tensor: tokens chosen by the prefill (row 0) and each decode step since."""
+        out = torch.empty(n_steps, B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_read_history(self._ctx, N.ptr(out), B, n_steps, self._stream()), "vcla_read_history")
+        return out
+
     def reset(self):
         with torch.cuda.device(self.device):
             N.check(self.lib.vcla_reset(self._ctx, self._stream()), "vcla_reset")

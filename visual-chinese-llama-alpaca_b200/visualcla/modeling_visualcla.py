@@ -409,6 +409,15 @@ class VisualCLAModel:
         all_logits: List[torch.Tensor] = []
 
         last, first_tok, _ = eng.prefill(input_ids, mode, rows, all_logits=False, last_logits=need_logits)
+        if not need_logits and not eos and not crit:
+            # pure greedy, fixed length: graph replays only; tokens come from the device-side history the graph appends to
+            tok.copy_(first_tok)
+            for _ in range(1, max_new):
+                eng.decode_step(tok, tok, None)
+            result = eng.read_history(B, max_new).t().to(torch.int64)
+            if getattr(gc, "return_dict_in_generate", False):
+                return SimpleNamespace(sequences=result, logits=None, scores=None)
+            return result
         finished = torch.zeros(B, dtype=torch.bool, device=dev)
         n_done = 0
         for step in range(max_new):
