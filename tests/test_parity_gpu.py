@@ -156,6 +156,15 @@ def test_mid_config_vs_oracle():
     assert nbad == 0, f"free-running: {nbad} decisive tokens differ before the first divergence ({ndec}/{ntot} decisive)"
 
 
+def test_long_context_vs_oracle():
+    """BASELINE configs[4] in miniature: long prompt (S = 64 + 900), multi-page KV cache, 4-way split-KV decode attention
+    (max_seq >= 1536 selects 4 KV splits), causal prefill attention over 16 KV tiles."""
+    cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=2, t_vocab=3001)
+    m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 11, 2, 900, 12, 1600)
+    assert err <= LOGIT_TOL, f"teacher-forced logits rel err {err:.3e}"
+    assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
+
+
 def test_batch_invariance_row_for_row():
     """DP correctness premise: a sample's tokens do not depend on what else is in the batch."""
     cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=2, t_vocab=2003)

@@ -256,6 +256,10 @@ __global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const De
         qv += __ldcg(row + h * HD + d);
         if (owns_new) { kv += __ldcg(row + T + h * HD + d); vv += __ldcg(row + 2 * T + h * HD + d); }
       }
+      if (c.rstd != nullptr) {          // deferred RMSNorm scale of the projection input (a row scalar commutes with the GEMM)
+        const float rs = __ldcg(c.rstd + b);
+        qv *= rs; kv *= rs; vv *= rs;
+      }
       s_q[d] = qv; s_k[d] = kv; s_v[d] = vv;
     }
     __syncthreads();

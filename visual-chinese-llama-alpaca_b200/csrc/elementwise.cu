@@ -219,6 +219,43 @@ int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vo
   return 0;
 }
 
+// decode step entry (one CTA per sequence): embedding row -> fp32 residual, bf16 GEMM operand pre-multiplied by the first
+// layer's RMSNorm weight, and the row's deferred scale 1/rms
+__global__ void dec_embed_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ resid,
+                                 const float* __restrict__ norm_w, float eps, bf16* __restrict__ xw, float* __restrict__ rstd) {
+  __shared__ float red[32];
+  TraceScope trace(13);
+  pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
+  pdl_wait();
+  trace.dep();
+  const int b = blockIdx.x;
+  int id = ids[b];
+  if (id < 0 || id >= vocab) id = 0;
+  const bf16* src = table + (size_t)id * D;
+  float q = 0.f;
+  for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(w4[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    *reinterpret_cast<float4*>(resid + (size_t)b * D + i) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(resid + (size_t)b * D + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    const float4 w0 = *reinterpret_cast<const float4*>(norm_w + i), w1 = *reinterpret_cast<const float4*>(norm_w + i + 4);
+    *reinterpret_cast<uint4*>(xw + (size_t)b * D + i) = make_uint4(pack_bf16x2(f[0] * w0.x, f[1] * w0.y), pack_bf16x2(f[2] * w0.z, f[3] * w0.w),
+                                                                    pack_bf16x2(f[4] * w1.x, f[5] * w1.y), pack_bf16x2(f[6] * w1.z, f[7] * w1.w));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += f[j] * f[j];
+  }
+  q = block_sum(q, red);
+  if (threadIdx.x == 0) rstd[b] = rsqrtf(q / D + eps);
+}
+int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps, bf16* xw, float* rstd, cudaStream_t st) {
+  if (D % 8) { set_error("dec_embed: D %% 8 != 0"); return -1; }
+  VCLA_LAUNCH(dec_embed_kernel, dim3(B), dim3(256), 0, st, ids, D, table, vocab, resid, norm_w, eps, xw, rstd);
+  return 0;
+}
+
 __global__ void scatter_image_rows_kernel(const float* __restrict__ img, int nq, int D, const int32_t* __restrict__ row_start, int S, float* __restrict__ dst) {
   const int q = blockIdx.x, b = blockIdx.y;
   const int rs = row_start[b];
@@ -428,7 +465,7 @@ int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf
 // logits + argmax: stage 1 per (vocab chunk, b) -> candidate ; stage 2 per b
 constexpr int kArgChunks = 32;
 __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits, int ws_rows, int ldp, int V, float* __restrict__ logits,
-                                  int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+                                  int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx, const float* __restrict__ rstd) {
   __shared__ float sv[32];
   __shared__ int si[32];
   TraceScope trace(10);
@@ -436,13 +473,15 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
   pdl_wait();
   trace.dep();
   const int b = blockIdx.y, ch = blockIdx.x;
+  const float rs = rstd ? __ldcg(rstd + b) : 1.f;       // deferred RMSNorm scale of the final norm
   const int per = (V + kArgChunks - 1) / kArgChunks;
   const int v0 = ch * per, v1 = min(V, v0 + per);
   float best = -INFINITY;
   int bi = 0x7fffffff;
   for (int v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
     float x = 0.f;
-    for (int s = 0; s < splits; ++s) x += partial[((size_t)s * ws_rows + b) * (size_t)ldp + v];
+    for (int s = 0; s < splits; ++s) x += __ldcg(partial + ((size_t)s * ws_rows + b) * (size_t)ldp + v);
+    x *= rs;
     if (logits) logits[(size_t)b * ld_logits + v] = x;
     if (x > best) { best = x; bi = v; }   // strided order: smaller index kept on ties via the reduction below
   }
@@ -498,9 +537,9 @@ int argmax_scratch_init(int max_batch) {
   return 0;
 }
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok,
-                      int32_t* history, const int32_t* step_idx, cudaStream_t st) {
+                      int32_t* history, const int32_t* step_idx, const float* rstd, cudaStream_t st) {
   if (g_cand_cap < B) { set_error("argmax scratch too small (%d < %d)", g_cand_cap, B); return -1; }
-  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx);
+  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx, rstd);
   VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok, history, step_idx);
   return 0;
 }

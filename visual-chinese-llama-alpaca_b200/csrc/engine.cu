@@ -107,7 +107,9 @@ struct vcla_ctx {
   float *ws_qkv = nullptr, *ws_o = nullptr, *ws_gu = nullptr, *ws_d = nullptr, *ws_lm = nullptr;
   float* attn_scratch = nullptr; int32_t* attn_counters = nullptr;
   int32_t* d_tok = nullptr;
-  int32_t *tok_hist = nullptr, *step_idx = nullptr;   // tokens of every step since the last prefill, appended by the argmax kernel
+  int32_t *tok_hist = nullptr, *step_idx = nullptr;
+  float *d_rstd = nullptr, *d_ssq = nullptr; int32_t *cnt_o = nullptr, *cnt_gu = nullptr, *cnt_d = nullptr;   // fused split-K consumers (decode)
+  int fused_decode = 1;   // tokens of every step since the last prefill, appended by the argmax kernel
   int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
   int l2_prefetch_kb = 0;    // decode GEMMs: weight k-blocks per CTA prefetched into L2 during the dependency wait (VCLA_L2_PREFETCH_KB).
                              // Measured harmful on B200 (0/8/16/24/48 -> 3142/3226/3349/3390/3437 us per step: the prefetch traffic delays
@@ -292,6 +294,11 @@ void layout_activations(vcla_ctx* c) {
   c->d_tok = a_alloc<int32_t>(c, Bp);
   c->tok_hist = a_alloc<int32_t>(c, (size_t)(g.max_seq + 2) * Bp);
   c->step_idx = a_alloc<int32_t>(c, 16);
+  c->d_rstd = a_alloc<float>(c, Bp);
+  c->d_ssq = a_alloc<float>(c, Bp * ((T + 127) / 128));
+  c->cnt_o = a_alloc<int32_t>(c, (T + 127) / 128 + 1);
+  c->cnt_d = a_alloc<int32_t>(c, (T + 127) / 128 + 1);
+  c->cnt_gu = a_alloc<int32_t>(c, (2 * F + 127) / 128 + 1);
   c->page_table = a_alloc<int32_t>(c, (size_t)g.max_batch * c->pages_per_seq);
   c->seq_len = a_alloc<int32_t>(c, g.max_batch);
   c->img_row_default = a_alloc<int32_t>(c, g.max_batch);
@@ -370,6 +377,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   c->sp_d = pick_splits(g.t_hidden, g.t_ffn);
   c->sp_lm = pick_splits(g.t_vocab, g.t_hidden);
   if (const char* e = getenv("VCLA_L2_PREFETCH_KB")) c->l2_prefetch_kb = atoi(e);
+  if (const char* e = getenv("VCLA_FUSED_DECODE")) c->fused_decode = atoi(e);
   c->kv_splits = g.max_seq >= 1536 ? 4 : (g.max_seq >= 768 ? 2 : 1);   // context-driven minimum; raised per call for small batches
 
   if (gemm_init()) { delete c; return -1; }
@@ -603,9 +611,10 @@ int vcla_vision_encode(vcla_ctx* c, const void* pixels, int pixel_dtype, int B, 
 // -------------------------------------------------------------------------------------------------
 // prefill
 // -------------------------------------------------------------------------------------------------
-static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X, int B, int splits, float* ws, cudaStream_t st) {
+static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X, int B, int splits, float* ws, cudaStream_t st, const GemmFix* fix = nullptr) {
   GemmCall g; g.A = W; g.B = X; g.M = n_out; g.N = B; g.K = K; g.lda = K; g.ldb = K; g.mode = GEMM_PARTIAL_F32; g.out = ws; g.ldo = n_out;
   g.splits = splits; g.ws_rows = B; g.weights_are_A = 1; g.l2_prefetch_kb = c->l2_prefetch_kb;
+  if (fix) g.fix = *fix;
   count(c); return gemm_tc(g, st);
 }
 
@@ -615,7 +624,7 @@ static int lm_head_last(vcla_ctx* c, int B, float* logits_dev, int32_t* tok_dev,
   count(c); if (dec_resid_norm(nullptr, 0, B, c->d_resid, B, g.t_hidden, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, g.t_hidden, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
   count(c, 2);
-  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, c->tok_hist, c->step_idx, st);
+  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, c->tok_hist, c->step_idx, nullptr, st);
 }
 
 int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, float* logits_all,
@@ -665,20 +674,19 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
 // -------------------------------------------------------------------------------------------------
 // decode
 // -------------------------------------------------------------------------------------------------
-static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
+// Legacy schedule (8 kernels per layer: separate norm / silu consumers).  Kept for A/B measurements (VCLA_FUSED_DECODE=0).
+static int decode_enqueue_unfused(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
   const vcla_config& g = c->cfg;
   const int TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
   count(c); if (embed_tokens_i32(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, st)) return -1;
   const float scale = 1.0f / sqrtf(128.f);
   for (int i = 0; i < g.t_layers; ++i) {
     const TextLayer& L = c->tl[i];
-    // residual += previous layer's down-projection partials ; xn = rmsnorm(residual)
     count(c); if (dec_resid_norm(i == 0 ? nullptr : c->ws_d, c->sp_d, B, c->d_resid, B, TH, L.ln1, g.t_eps, c->d_xn, st)) return -1;
     if (swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st)) return -1;
     DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
     a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
     a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta;
-    // one wave of 256-thread CTAs (3 per SM): enough CTAs to cover the SMs, never more than fit at once
     { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
     count(c); if (attention_decode(a, st)) return -1;
     if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st)) return -1;
@@ -689,7 +697,41 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
   }
   count(c); if (dec_resid_norm(c->ws_d, c->sp_d, B, c->d_resid, B, TH, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
-  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, c->tok_hist, c->step_idx, st)) return -1;
+  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, c->tok_hist, c->step_idx, nullptr, st)) return -1;
+  count(c); if (advance_seq(c->seq_len, B, 1, c->step_idx, st)) return -1;
+  return 0;
+}
+
+// Decode step, 5 kernels per layer:  QKV GEMM -> attention(+reduce, rstd, RoPE, append) -> O GEMM [+residual, norm weight, sum sq]
+//   -> gate/up GEMM [+rstd, SiLU*mul] -> down GEMM [+residual, next norm weight, sum sq].  The bracketed consumers run inside
+// the GEMM, in the CTA whose split-K partial completes a tile; RMSNorm's per-row scale is deferred to the next consumer.
+static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
+  if (!c->fused_decode) return decode_enqueue_unfused(c, tok_in, B, logits, tok_out, st);
+  const vcla_config& g = c->cfg;
+  const int TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
+  count(c); if (dec_embed(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, c->tl[0].ln1, g.t_eps, c->d_xn, c->d_rstd, st)) return -1;
+  const float scale = 1.0f / sqrtf(128.f);
+  GemmFix fr;   // residual + deferred norm
+  fr.mode = FIX_RESID; fr.resid = c->d_resid; fr.xw_out = c->d_xn; fr.ssq = c->d_ssq; fr.rstd_out = c->d_rstd; fr.inv_dim = 1.0f / (float)TH; fr.eps = g.t_eps;
+  GemmFix fs;   // SwiGLU
+  fs.mode = FIX_SWIGLU; fs.tile_counters = c->cnt_gu; fs.rstd_in = c->d_rstd; fs.h_out = c->d_h;
+  for (int i = 0; i < g.t_layers; ++i) {
+    const TextLayer& L = c->tl[i];
+    if (swap_gemm(c, L.wqkv, 3 * TH, TH, c->d_xn, B, c->sp_qkv, c->ws_qkv, st)) return -1;
+    DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
+    a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
+    a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta; a.rstd = c->d_rstd;
+    // one wave of 256-thread CTAs (3 per SM): enough CTAs to cover the SMs, never more than fit at once
+    { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
+    count(c); if (attention_decode(a, st)) return -1;
+    fr.tile_counters = c->cnt_o; fr.norm_w = L.ln2;
+    if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st, &fr)) return -1;
+    if (swap_gemm(c, L.wgu, 2 * F, TH, c->d_xn, B, c->sp_gu, c->ws_gu, st, &fs)) return -1;
+    fr.tile_counters = c->cnt_d; fr.norm_w = (i + 1 < g.t_layers) ? c->tl[i + 1].ln1 : c->final_norm;
+    if (swap_gemm(c, L.wd, TH, F, c->d_h, B, c->sp_d, c->ws_d, st, &fr)) return -1;
+  }
+  if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
+  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, c->tok_hist, c->step_idx, c->d_rstd, st)) return -1;
   count(c); if (advance_seq(c->seq_len, B, 1, c->step_idx, st)) return -1;
   return 0;
 }

@@ -35,6 +35,24 @@ enum GemmMode {
   GEMM_PARTIAL_F32 = 3,  // swap-AB split-K partials: ws[(split*ws_rows + col) * ldo + row] = acc   (row = A row)
 };
 enum Act { ACT_NONE = 0, ACT_QUICK_GELU = 1, ACT_GELU_ERF = 2 };
+// Fused consumer of the split-K partials, run by the CTA that completes a tile ("last arriver", GEMM_PARTIAL_F32 only):
+//   FIX_RESID : r = resid[b,n] + sum_s partial ; resid = r ; xw[b,n] = bf16(r * norm_w[n]) ; ssq[b, tile] = sum_n r^2 ;
+//               the CTA that completes the LAST tile also writes rstd[b] = rsqrt(sum_tiles ssq / N + eps).
+//               (RMSNorm with the per-row scale deferred to the next consumer: a row scalar commutes with the next GEMM.)
+//   FIX_SWIGLU: g,u = rstd[b] * sum_s partial (rows interleaved [32 gate | 32 up]) ; h[b,j] = bf16(silu(g) * u)
+enum FixMode { FIX_NONE = 0, FIX_RESID = 1, FIX_SWIGLU = 2 };
+struct GemmFix {
+  int mode = FIX_NONE;
+  int32_t* tile_counters = nullptr;   // [m_tiles + 1] zero between launches; the last entry counts finished tiles
+  float* resid = nullptr;             // [B, N_out] fp32 (FIX_RESID)
+  const float* norm_w = nullptr;      // [N_out]
+  bf16* xw_out = nullptr;             // [B, N_out]
+  float* ssq = nullptr;               // [B, m_tiles] scratch
+  float* rstd_out = nullptr;          // [B]
+  float inv_dim = 0.f, eps = 0.f;
+  const float* rstd_in = nullptr;     // [B] (FIX_SWIGLU)
+  bf16* h_out = nullptr;              // [B, N_out/2]
+};
 
 struct GemmCall {
   const bf16* A = nullptr;   // [M, K], row pitch lda elements
@@ -59,6 +77,7 @@ struct GemmCall {
   int weights_are_A = 0;     // cache-policy hint: A is the streamed-once operand (decode)
   int bn = 0;                // tile N override (0 = auto)
   int l2_prefetch_kb = 0;    // k-blocks of the weight operand each CTA prefetches into L2 while it waits for its dependency
+  GemmFix fix;               // fused consumer of the split-K partials (decode)
 };
 int gemm_tc(const GemmCall& c, cudaStream_t st);
 // correctness reference for the tests only (CUDA-core, one thread per output)
@@ -94,6 +113,7 @@ struct DecodeAttnCall {
   int32_t* counters = nullptr;         // [B][H]
   int B = 0, H = 0, HD = 0, kv_splits = 1;
   float scale = 1.f, rope_theta = 10000.f;
+  const float* rstd = nullptr;         // [B] deferred RMSNorm scale of the QKV projection's input (null: 1)
 };
 int attention_decode(const DecodeAttnCall& c, cudaStream_t st);
 
@@ -130,7 +150,10 @@ int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, 
 int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st);
 // logits[b, :] = sum_s partial[s][b][:V] ; tok[b] = argmax (first max wins, like torch.argmax)
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits,
-                      int32_t* tok, int32_t* history, const int32_t* step_idx, cudaStream_t st);
+                      int32_t* tok, int32_t* history, const int32_t* step_idx, const float* rstd, cudaStream_t st);
+// decode step entry: resid[b,:] = table[ids[b]] ; xw = bf16(resid * norm_w) ; rstd[b] = rsqrt(mean(resid^2) + eps)
+int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps,
+              bf16* xw, float* rstd, cudaStream_t st);
 int advance_seq(int32_t* seq_len, int B, int by, int32_t* step_idx, cudaStream_t st);
 int rope_init(int max_pos, int head_dim, float theta);
 int argmax_scratch_init(int max_batch);
