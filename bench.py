@@ -33,7 +33,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "hf-cuda"])
+    ap.add_argument("--hf-dtype", default="float16", choices=["float16", "bfloat16"], help="hf-cuda arm: the reference ships fp16 (inference.py:47)")
     ap.add_argument("--batch-per-gpu", type=int, default=8)
     ap.add_argument("--new-tokens", type=int, default=N_NEW)
     ap.add_argument("--prompt-tokens", type=int, default=T_TEXT, help="text tokens per prompt (64 = configs[1]; 128 = configs[2])")
@@ -325,10 +326,72 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# informational arm: the reference's CUDA path = HF CLIPVisionModel + the Resampler arithmetic in torch + HF
+# LlamaForCausalLM.generate(inputs_embeds=...) on the same GPU, same shapes, random weights (north star's 8x denominator).
+# /root/reference is not on the GPU box, so the composite module is re-assembled from the very HF classes it calls
+# (modeling_visualcla.py:346-391) and the oracle's torch restatement of the in-repo Resampler, run on the device.
+# ----------------------------------------------------------------------------------------------------------------
+def run_hf_cuda(args):
+    import torch
+    from transformers import LlamaConfig, LlamaForCausalLM, GenerationConfig
+    from transformers.models.clip.modeling_clip import CLIPVisionConfig, CLIPVisionModel
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import visualcla_oracle as O
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dt = getattr(torch, args.hf_dtype)
+    B, n_new, T = args.batch_per_gpu, args.new_tokens, args.prompt_tokens
+    cfg = O.PathConfig()
+    torch.cuda.set_device(0)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dt)
+    with torch.device("cuda"):
+        llama = LlamaForCausalLM(LlamaConfig(vocab_size=cfg.t_vocab, hidden_size=cfg.t_hidden, intermediate_size=cfg.t_ffn, num_hidden_layers=cfg.t_layers,
+                                             num_attention_heads=cfg.t_heads, num_key_value_heads=cfg.t_heads, rms_norm_eps=cfg.t_eps,
+                                             max_position_embeddings=2048, tie_word_embeddings=False, pad_token_id=0, bos_token_id=1, eos_token_id=2)).eval()
+        clip = CLIPVisionModel(CLIPVisionConfig(hidden_size=cfg.v_hidden, intermediate_size=cfg.v_ffn, num_hidden_layers=cfg.v_layers,
+                                                num_attention_heads=cfg.v_heads, image_size=cfg.v_image, patch_size=cfg.v_patch, hidden_act="quick_gelu")).eval()
+        w = {n: torch.randn(*sh) * std + mean for n, sh, std, mean in O.weight_specs(cfg) if n.startswith(("visual_resampler.", "image_projection_layer."))}
+    torch.set_default_dtype(old)
+    px_h, ids_h = synth_inputs(B, T=T)
+    px, ids = px_h.cuda().to(dt), ids_h.cuda()
+    gc = GenerationConfig(do_sample=False, max_new_tokens=n_new, min_new_tokens=n_new, eos_token_id=None, pad_token_id=0)
+
+    @torch.no_grad()
+    def step():
+        emb = llama.get_input_embeddings()(ids)
+        vit = clip(pixel_values=px)[0]
+        post = clip.vision_model.post_layernorm(vit)
+        img = O.project(w, O.resampler_forward(w, cfg, post))
+        x = torch.cat([emb[:, :2], img.to(dt), emb[:, 2:]], dim=1)
+        mask = torch.ones(x.shape[:2], dtype=torch.long, device="cuda")
+        return llama.generate(inputs_embeds=x, attention_mask=mask, generation_config=gc)
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        out = step()
+    assert out.shape == (B, n_new), out.shape
+    torch.cuda.synchronize()
+    k = max(1, min(args.steps, 3))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(k):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / k
+    print(json.dumps({"impl": "hf-cuda", "metric": METRIC, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": k, "warmup": 1, "ms_per_step": ms,
+                      "higher_is_better": True, "dtype": args.hf_dtype, "data": "synthetic, random weights",
+                      "config": {"workload": f"batch {B}, {T}-token prompts + 64 image tokens, {n_new} greedy tokens; HF CLIPVisionModel + torch Resampler + "
+                                             f"HF LlamaForCausalLM.generate(inputs_embeds) eager/SDPA, transformers {__import__('transformers').__version__}"}}), flush=True)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "hf-cuda":
+        run_hf_cuda(args)
     else:
         run_native(args)
 

@@ -165,6 +165,65 @@ def test_long_context_vs_oracle():
     assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
 
 
+def test_fused_decode_schedule_matches(monkeypatch):
+    """VCLA_FUSED_DECODE=1 (split-K last-arriver fixup inside the GEMM, deferred RMSNorm scale) is an alternative decode
+    schedule: it must satisfy the same parity bar, and agree with the default schedule on decisive tokens."""
+    cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=3, t_vocab=2003)
+    monkeypatch.setenv("VCLA_FUSED_DECODE", "1")
+    m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 13, 3, 40, 20, 160)
+    assert err <= LOGIT_TOL, f"teacher-forced logits rel err {err:.3e}"
+    assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
+
+
+def test_chat_api_on_device():
+    """The reference's chat()/chat_in_stream() entry points (ref: modeling_utils.py:143-247) drive the CUDA path end to end
+    (stub tokenizer / image processor: no tokenizer files exist offline)."""
+    import visualcla
+    from transformers import GenerationConfig
+
+    cfg = O.tiny_config()
+    m = visualcla.VisualCLAModel.from_synthetic(cfg.to_dict(), seed=0, max_batch=1, max_seq=256)
+    s0, s1, s2, s3 = O.special_ids(cfg)
+
+    class Tok:
+        bos_token, pad_token, bos_token_id, eos_token_id = "<s>", "<pad>", 1, 2
+        img_start_token, img_end_token, img_token = "<img>", "</img>", "<img_token>"
+        img_start_token_id, img_end_token_id, img_token_id = s0, s1, s3
+
+        def __call__(self, text, return_tensors=None, add_special_tokens=None):
+            from transformers import BatchEncoding
+            ids, i = [], 0
+            special = {"<s>": 1, "<img>": s0, "</img>": s1, "<img_token>": s3}
+            while i < len(text):
+                for k, v in special.items():
+                    if text.startswith(k, i):
+                        ids.append(v); i += len(k); break
+                else:
+                    ids.append(3 + (ord(text[i]) % 900)); i += 1
+            t = torch.tensor([ids])
+            return BatchEncoding({"input_ids": t, "attention_mask": torch.ones_like(t)})
+
+        def decode(self, ids, skip_special_tokens=True):
+            return " ".join(str(int(x)) for x in ids)
+
+    m.tokenizer, m.image_at_head, m.num_patch = Tok(), False, cfg.r_queries
+    m.image_processor = lambda img, return_tensors=None: types.SimpleNamespace(pixel_values=torch.randn(1, 3, cfg.v_image, cfg.v_image))
+    px = torch.randn(1, 3, cfg.v_image, cfg.v_image)
+    gc = GenerationConfig(do_sample=False, max_new_tokens=5, eos_token_id=None, pad_token_id=0)
+    hist = []
+    resp, hist = visualcla.chat(m, image=px, text="hello", history=hist, generation_config=gc)
+    assert len(resp.split()) == 5 and hist[0].get("first_instruction") and hist[-1]["type"] == "response"
+    resp2, hist = visualcla.chat(m, image=px, text="more", history=hist, generation_config=gc)       # multi-turn: image block only in turn 1
+    assert len(hist) == 4
+    # default (sampling) config path: temperature/top-k/top-p/repetition penalty/no-repeat-ngram on the returned logits
+    gs = GenerationConfig(do_sample=True, top_k=40, top_p=0.9, temperature=0.5, repetition_penalty=1.1, no_repeat_ngram_size=15,
+                          max_new_tokens=6, eos_token_id=None, pad_token_id=0)
+    resp3, _ = visualcla.chat(m, image=px, text="again", history=[], generation_config=gs)
+    assert len(resp3.split()) == 6
+    chunks = list(visualcla.chat_in_stream(m, image=px, text="stream", history=[], generation_config=gc))
+    assert len(chunks) == 5 and len(chunks[-1][0].split()) == 5 and chunks[-1][1][-1]["type"] == "response"
+
+
 def test_batch_invariance_row_for_row():
     """DP correctness premise: a sample's tokens do not depend on what else is in the batch."""
     cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=2, t_vocab=2003)

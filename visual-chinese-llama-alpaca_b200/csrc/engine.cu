@@ -109,7 +109,8 @@ struct vcla_ctx {
   int32_t* d_tok = nullptr;
   int32_t *tok_hist = nullptr, *step_idx = nullptr;
   float *d_rstd = nullptr, *d_ssq = nullptr; int32_t *cnt_o = nullptr, *cnt_gu = nullptr, *cnt_d = nullptr;   // fused split-K consumers (decode)
-  int fused_decode = 1;   // tokens of every step since the last prefill, appended by the argmax kernel
+  int fused_decode = 0;   // VCLA_FUSED_DECODE=1: 5-kernel/layer schedule with in-GEMM split-K fixup. Correct (parity-tested) but measured slower
+                          // on B200 (3.96 vs 3.32 ms/token at B=8): the fence->atomic->reload chain per tile outlasts a kernel boundary.   // tokens of every step since the last prefill, appended by the argmax kernel
   int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
   int l2_prefetch_kb = 0;    // decode GEMMs: weight k-blocks per CTA prefetched into L2 during the dependency wait (VCLA_L2_PREFETCH_KB).
                              // Measured harmful on B200 (0/8/16/24/48 -> 3142/3226/3349/3390/3437 us per step: the prefetch traffic delays
