@@ -402,8 +402,11 @@ class VisualCLAModel:
         dev = eng.device
         key = (B, need_logits)
         if key not in self._tok_buf:
-            self._tok_buf[key] = (torch.zeros(B, dtype=torch.int32, device=dev),
-                                  torch.empty(B, eng.vocab, dtype=torch.float32, device=dev) if need_logits else None)
+            # persistent step buffers (their addresses key the captured CUDA graph).  chat() runs under torch.inference_mode and
+            # chat_in_stream's worker thread does not: allocate them as ordinary tensors so both may update them in place.
+            with torch.inference_mode(False):
+                self._tok_buf[key] = (torch.zeros(B, dtype=torch.int32, device=dev),
+                                      torch.empty(B, eng.vocab, dtype=torch.float32, device=dev) if need_logits else None)
         tok, logits = self._tok_buf[key]
         out = torch.full((B, max_new), pad, dtype=torch.int64, device=dev)
         all_logits: List[torch.Tensor] = []
