@@ -209,43 +209,69 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
 // =================================================================================================
 // decode (hd = 128): grid (kv_splits, H, B), 128 threads
 // =================================================================================================
-constexpr int kMaxPagesPerSplit = 128;   // pages one CTA may touch (host checks max_seq / page_tokens / kv_splits)
-constexpr int kDecWarps = 8;   // 256 threads = 32 cached tokens in flight per CTA iteration; the host keeps B*H*kv_splits within one wave (3 CTAs/SM)
-__global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+constexpr int kDecWarps = 8;        // 256 threads
+constexpr int kDecStages = 3;       // KV pages in flight per CTA (3 x 32 KB at 64 tokens/page -> 2 CTAs per SM)
+constexpr int kDecMaxPT = 64;       // page_tokens supported by the smem ring
+
+// One CTA per (kv split, head, sequence).  The cached K/V rows of a head are contiguous per page (page_tokens x 128 bf16 =
+// 16 KB), so whole pages are streamed with TMA bulk copies (cp.async.bulk, mbarrier completion) into a 3-stage shared-memory
+// ring and the dot products / PV accumulation run out of shared memory: the kernel is bandwidth- instead of latency-bound
+// (the register-prefetch version had one DRAM round trip per 32 tokens per CTA).
+__global__ void __launch_bounds__(kDecWarps * 32, 2) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
                                                                      const float* __restrict__ rope_sin) {
   constexpr int HD = 128;
+  extern __shared__ __align__(128) uint8_t dsm[];      // [kDecStages][2][PT][HD] bf16
+  __shared__ __align__(8) uint64_t s_bar[kDecStages];
   __shared__ float s_q[HD];
   __shared__ float s_k[HD];
   __shared__ float s_v[HD];
   __shared__ float s_acc[kDecWarps][HD];
   __shared__ float s_m[kDecWarps], s_l[kDecWarps];
-  __shared__ int s_pages[kMaxPagesPerSplit];
   __shared__ int s_last;
 
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T = c.H * HD;
+  const int T = c.H * HD, PT = c.page_tokens;
+  const uint32_t stage_bytes = (uint32_t)PT * HD * 2 * 2;      // K page + V page
   TraceScope trace(4);
 
+  if (tid == 0) {
+    for (int s = 0; s < kDecStages; ++s) mbar_init(smem_u32(&s_bar[s]), 1);
+    fence_barrier_init();
+  }
   pdl_launch_dependents();
   pdl_wait();
   trace.dep();
+  __syncthreads();
 
   const int L = c.seq_len[b];          // tokens already cached; the new token gets index L
   const int n = L + 1;
   int chunk = (n + c.kv_splits - 1) / c.kv_splits;
-  chunk = (chunk + kDecWarps * 4 - 1) / (kDecWarps * 4) * (kDecWarps * 4);
+  chunk = (chunk + PT - 1) / PT * PT;                 // splits own whole pages
   const int t_begin = split * chunk;
   const int t_end = min(n, t_begin + chunk);
   const bool owns_new = (t_begin <= L) && (L < t_end);
+  const int c_end = min(t_end, L);                    // cached tokens of this CTA: [t_begin, c_end)
+  const int p0 = t_begin / PT;
+  const int npages = c_end > t_begin ? (c_end - t_begin + PT - 1) / PT : 0;
 
-  // ---- stage this CTA's page ids (independent of everything below: overlaps the partial-sum loads)
-  {
-    const int p0 = t_begin / c.page_tokens;
-    const int p1 = (min(t_end, L) + c.page_tokens - 1) / c.page_tokens;
-    for (int i = tid; i < p1 - p0 && i < kMaxPagesPerSplit; i += blockDim.x)
-      s_pages[i] = __ldg(c.page_table + (size_t)b * c.pages_per_seq + p0 + i);
+  auto issue_page = [&](int i) {                      // thread 0: request page i of this CTA into stage i % kDecStages
+    const int stage = i % kDecStages;
+    const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + p0 + i);
+    const int ntok = min(PT, c_end - (t_begin + i * PT));
+    const uint32_t bytes = (uint32_t)ntok * HD * 2;
+    const uint32_t bar = smem_u32(&s_bar[stage]);
+    const uint32_t dst = smem_u32(dsm) + stage * stage_bytes;
+    const bf16* ksrc = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * PT) * HD;
+    const bf16* vsrc = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * PT) * HD;
+    mbar_arrive_expect_tx(bar, 2 * bytes);
+    bulk_load_1d(dst, ksrc, bytes, bar);
+    bulk_load_1d(dst + (uint32_t)PT * HD * 2, vsrc, bytes, bar);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < npages && i < kDecStages; ++i) issue_page(i);   // the KV stream starts before the q reduction below
   }
+
   // ---- reduce the split-K partials of this head's q (and k, v if this CTA owns the new token); RoPE
   {
     const int d = tid & (HD - 1);
@@ -279,10 +305,10 @@ __global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const De
         const bf16 kb = __float2bfloat16(kr), vb = __float2bfloat16(vv);
         s_k[d] = __bfloat162float(kb);
         s_v[d] = __bfloat162float(vb);
-        const int page = c.page_table[(size_t)b * c.pages_per_seq + L / c.page_tokens];
-        const int slot = L % c.page_tokens;
-        bf16* kdst = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * c.page_tokens + slot) * HD;
-        bf16* vdst = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * c.page_tokens + slot) * HD;
+        const int page = c.page_table[(size_t)b * c.pages_per_seq + L / PT];
+        const int slot = L % PT;
+        bf16* kdst = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * PT + slot) * HD;
+        bf16* vdst = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * PT + slot) * HD;
         kdst[d] = kb;
         vdst[d] = vb;
       }
@@ -290,73 +316,62 @@ __global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const De
     __syncthreads();
   }
 
-  // ---- attention over cached tokens [t_begin, min(t_end, L)): 8 lanes per token, 16 dims per lane.
-  // Page ids of this CTA's token range were staged in smem by the prologue; K/V rows of the NEXT iteration are
-  // requested before the current one is reduced (register double buffer), so one DRAM latency is exposed per CTA
-  // instead of two per iteration.
+  // ---- attention over the cached tokens, page by page out of shared memory.  8 lanes per token; lane `sub` owns the 16 B
+  //      chunks `sub` and `sub + 8` of a 256 B row (dims [8 sub, 8 sub + 8) and [64 + 8 sub, 64 + 8 sub + 8)): a quarter warp
+  //      then touches 128 contiguous bytes -> conflict-free LDS.128.
   const int grp = lane >> 3, sub = lane & 7;
   const uint32_t gmask = 0xffu << (grp * 8);
   float qreg[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) qreg[i] = s_q[sub * 16 + i];
+  for (int i = 0; i < 8; ++i) { qreg[i] = s_q[sub * 8 + i]; qreg[8 + i] = s_q[64 + sub * 8 + i]; }
   float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 
-  const int c_end = min(t_end, L);
-  const int page0 = t_begin / c.page_tokens;
-  auto kv_ptr = [&](int t, int which) {
-    const int page = s_pages[t / c.page_tokens - page0];
-    const int slot = t % c.page_tokens;
-    return reinterpret_cast<const uint4*>(c.kv_pages + ((((size_t)page * 2 + which) * c.H + h) * c.page_tokens + slot) * HD + sub * 16);
-  };
-  __syncwarp();
-  int t = t_begin + warp * 4 + grp;
-  uint4 k0, k1, v0, v1;
-  if (t < c_end) {
-    const uint4* kp = kv_ptr(t, 0);
-    const uint4* vp = kv_ptr(t, 1);
-    k0 = __ldg(kp); k1 = __ldg(kp + 1); v0 = __ldg(vp); v1 = __ldg(vp + 1);
-  }
-  while (t < c_end) {
-    const int tn = t + kDecWarps * 4;
-    uint4 nk0, nk1, nv0, nv1;
-    if (tn < c_end) {
-      const uint4* kp = kv_ptr(tn, 0);
-      const uint4* vp = kv_ptr(tn, 1);
-      nk0 = __ldg(kp); nk1 = __ldg(kp + 1); nv0 = __ldg(vp); nv1 = __ldg(vp + 1);
-    }
-    const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-    const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    float sc = 0.f;
+  for (int i = 0; i < npages; ++i) {
+    const int stage = i % kDecStages;
+    const uint32_t parity = (uint32_t)((i / kDecStages) & 1);
+    mbar_wait(smem_u32(&s_bar[stage]), parity);
+    const int ntok = min(PT, c_end - (t_begin + i * PT));
+    const uint8_t* kbase = dsm + (size_t)stage * stage_bytes;
+    const uint8_t* vbase = kbase + (size_t)PT * HD * 2;
+    for (int tk = warp * 4 + grp; tk < ntok; tk += kDecWarps * 4) {
+      const uint4 k0 = *reinterpret_cast<const uint4*>(kbase + (size_t)tk * HD * 2 + sub * 16);
+      const uint4 k1 = *reinterpret_cast<const uint4*>(kbase + (size_t)tk * HD * 2 + 128 + sub * 16);
+      const uint4 v0 = *reinterpret_cast<const uint4*>(vbase + (size_t)tk * HD * 2 + sub * 16);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(vbase + (size_t)tk * HD * 2 + 128 + sub * 16);
+      const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+      const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float sc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float2 kf = unpack_bf16x2(kw[i]);
-      sc += qreg[2 * i] * kf.x + qreg[2 * i + 1] * kf.y;
-    }
-    // the 4 token groups of a warp may run different trip counts: reduce with the group's own 8-lane mask
-    sc += __shfl_xor_sync(gmask, sc, 1);
-    sc += __shfl_xor_sync(gmask, sc, 2);
-    sc += __shfl_xor_sync(gmask, sc, 4);
-    const float mn = fmaxf(m, sc);
-    const float cr = __expf(m - mn), p = __expf(sc - mn);
-    m = mn;
-    l = l * cr + p;
+      for (int j = 0; j < 8; ++j) {
+        const float2 kf = unpack_bf16x2(kw[j]);
+        sc += qreg[2 * j] * kf.x + qreg[2 * j + 1] * kf.y;
+      }
+      // token groups of a warp may run different trip counts: reduce with the group's own 8-lane mask
+      sc += __shfl_xor_sync(gmask, sc, 1);
+      sc += __shfl_xor_sync(gmask, sc, 2);
+      sc += __shfl_xor_sync(gmask, sc, 4);
+      const float mn = fmaxf(m, sc);
+      const float cr = __expf(m - mn), p = __expf(sc - mn);
+      m = mn;
+      l = l * cr + p;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float2 vf = unpack_bf16x2(vw[i]);
-      acc[2 * i] = acc[2 * i] * cr + p * vf.x;
-      acc[2 * i + 1] = acc[2 * i + 1] * cr + p * vf.y;
+      for (int j = 0; j < 8; ++j) {
+        const float2 vf = unpack_bf16x2(vw[j]);
+        acc[2 * j] = acc[2 * j] * cr + p * vf.x;
+        acc[2 * j + 1] = acc[2 * j + 1] * cr + p * vf.y;
+      }
     }
-    k0 = nk0; k1 = nk1; v0 = nv0; v1 = nv1;
-    t = tn;
+    __syncthreads();                                   // every warp is done with this stage
+    if (tid == 0 && i + kDecStages < npages) issue_page(i + kDecStages);
   }
   __syncwarp();
   // the new token (from smem), handled by warp 0 group 0 of the owning CTA
   if (owns_new && warp == 0 && grp == 0) {
     float sc = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sc += qreg[i] * s_k[sub * 16 + i];
+    for (int i = 0; i < 8; ++i) sc += qreg[i] * s_k[sub * 8 + i] + qreg[8 + i] * s_k[64 + sub * 8 + i];
     sc += __shfl_xor_sync(0x000000ffu, sc, 1);
     sc += __shfl_xor_sync(0x000000ffu, sc, 2);
     sc += __shfl_xor_sync(0x000000ffu, sc, 4);
@@ -365,7 +380,10 @@ __global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const De
     m = mn;
     l = l * cr + p;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = acc[i] * cr + p * s_v[sub * 16 + i];
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = acc[i] * cr + p * s_v[sub * 8 + i];
+      acc[8 + i] = acc[8 + i] * cr + p * s_v[64 + sub * 8 + i];
+    }
   }
   __syncwarp();
   // ---- merge the 4 token groups of a warp (lanes with equal `sub` hold the same dims)
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(kDecWarps * 32, 3) attn_decode_kernel(const De
   }
   if (grp == 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s_acc[warp][sub * 16 + i] = acc[i];
+    for (int i = 0; i < 8; ++i) { s_acc[warp][sub * 8 + i] = acc[i]; s_acc[warp][64 + sub * 8 + i] = acc[8 + i]; }
     if (sub == 0) { s_m[warp] = m; s_l[warp] = l; }
   }
   __syncthreads();
@@ -442,12 +460,22 @@ VCLA_DEFINE_TRACE_SETTER(trace_set_attention)
 const float* rope_cos_table();
 const float* rope_sin_table();
 
+int attention_decode_init() {
+  static bool done = false;
+  if (done) return 0;
+  VCLA_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecStages * kDecMaxPT * 128 * 2 * 2));
+  done = true;
+  return 0;
+}
+
 int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   if (c.HD != 128) { set_error("attention_decode: head dim %d unsupported (128)", c.HD); return -1; }
+  if (c.page_tokens > kDecMaxPT || c.page_tokens % 8 != 0) { set_error("attention_decode: page_tokens %d unsupported (<= %d, multiple of 8)", c.page_tokens, kDecMaxPT); return -1; }
   if (rope_cos_table() == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
-  if ((c.pages_per_seq + c.kv_splits - 1) / c.kv_splits + 2 > kMaxPagesPerSplit) { set_error("attention_decode: context too long for %d KV splits", c.kv_splits); return -1; }
+  if (attention_decode_init()) return -1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(kDecWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(kDecWarps * 32);
+  cfg.dynamicSmemBytes = (size_t)kDecStages * c.page_tokens * 128 * 2 * 2; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;
   if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }

@@ -365,6 +365,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   if (g.v_image % g.v_patch) return bad("image size must be a multiple of the patch size");
   if (g.max_batch < 1 || g.max_seq < 1 || g.max_prefill_tokens < 1) return bad("capacities must be positive");
   if (g.max_seq > 1 << 20) return bad("max_seq too large");
+  if (g.page_tokens > 64 || g.page_tokens % 8) return bad("page_tokens must be a multiple of 8 and <= 64");
   c->v_tokens = (g.v_image / g.v_patch) * (g.v_image / g.v_patch) + 1;
   c->kpatch = 3 * g.v_patch * g.v_patch;
   c->kpad = (c->kpatch + 63) / 64 * 64;
@@ -406,7 +407,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   cudaMemcpy(c->page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice);
   std::vector<int32_t> two(g.max_batch, 2);
   cudaMemcpy(c->img_row_default, two.data(), two.size() * 4, cudaMemcpyHostToDevice);
-  if (rope_init(g.max_seq + 1, 128, g.rope_theta) || argmax_scratch_init(64)) { vcla_destroy(c); return -1; }
+  if (rope_init(g.max_seq + 1, 128, g.rope_theta) || argmax_scratch_init(64) || attention_decode_init()) { vcla_destroy(c); return -1; }
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("vcla_create: device error %s", cudaGetErrorString(cudaGetLastError())); vcla_destroy(c); return -1; }
   *out = c;
   return 0;
@@ -722,7 +723,7 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
     DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
     a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
     a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta; a.rstd = c->d_rstd;
-    // one wave of 256-thread CTAs (3 per SM): enough CTAs to cover the SMs, never more than fit at once
+    // enough CTAs to cover the SMs for small batches; long contexts split so a CTA streams <= ~12 pages
     { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
     count(c); if (attention_decode(a, st)) return -1;
     fr.tile_counters = c->cnt_o; fr.norm_w = L.ln2;

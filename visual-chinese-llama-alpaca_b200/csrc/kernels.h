@@ -116,6 +116,7 @@ struct DecodeAttnCall {
   const float* rstd = nullptr;         // [B] deferred RMSNorm scale of the QKV projection's input (null: 1)
 };
 int attention_decode(const DecodeAttnCall& c, cudaStream_t st);
+int attention_decode_init();   // sets the dynamic-smem attribute (call outside graph capture)
 
 // ------------------------------------------------------------------------------------------
 // normalisation / elementwise / data movement
