@@ -399,16 +399,9 @@ dec_resid_norm_kernel(const float* __restrict__ partial, int splits, int ws_rows
     const int col = c0 + i;
     float4 v = *reinterpret_cast<const float4*>(resid + (size_t)b * D + col);
     if (partial) {
-      // all split-K partials of this column group are requested at once (one L2 round trip), then summed in order
-      constexpr int kMaxSplits = 24;
-      float4 pv[kMaxSplits];
-#pragma unroll
-      for (int s = 0; s < kMaxSplits; ++s)
-        if (s < splits) pv[s] = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * ws_rows + b) * D + col));
-#pragma unroll
-      for (int s = 0; s < kMaxSplits; ++s)
-        if (s < splits) { v.x += pv[s].x; v.y += pv[s].y; v.z += pv[s].z; v.w += pv[s].w; }
-      for (int s = kMaxSplits; s < splits; ++s) {
+      // (issuing all <= 24 partial loads at once was measured slower in situ: 6.96 vs 5.40 us after o_proj)
+#pragma unroll 4
+      for (int s = 0; s < splits; ++s) {
         const float4 p = __ldcg(reinterpret_cast<const float4*>(partial + ((size_t)s * ws_rows + b) * D + col));
         v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
       }
