@@ -106,3 +106,26 @@ def test_iteratorize_streams_and_stops():
             if v == 3:
                 break
     assert seen == [0, 1, 2, 3]
+
+
+def test_lora_key_plan_and_fold():
+    """Key normalisation of the reference's adapter_model.bin layout (ref convert_ckpt_for_tgwebui.py:46-71) + the fold math."""
+    from visualcla import lora
+    keys = ["base_model.model.text_model.model.layers.0.self_attn.q_proj.lora_A.weight",
+            "base_model.model.text_model.model.layers.0.self_attn.q_proj.lora_B.weight",
+            "base_model.model.vision_model.vision_model.encoder.layers.3.mlp.fc1.lora_A.default.weight",
+            "base_model.model.vision_model.vision_model.encoder.layers.3.mlp.fc1.lora_B.default.weight",
+            "base_model.model.text_model.model.embed_tokens.modules_to_save.default.weight",
+            "base_model.model.text_model.lm_head.weight",
+            "base_model.model.visual_resampler.query_embeddding",
+            "base_model.model.image_projection_layer.bias"]
+    pairs, full = lora.plan(keys)
+    assert set(pairs) == {"text_model.model.layers.0.self_attn.q_proj.weight", "vision_model.vision_model.encoder.layers.3.mlp.fc1.weight"}
+    assert set(full) == {"text_model.model.embed_tokens.weight", "text_model.lm_head.weight", "visual_resampler.query_embeddding",
+                         "image_projection_layer.bias"}
+    with pytest.raises(ValueError):
+        lora.plan(keys[:1])
+    g = torch.Generator().manual_seed(0)
+    W, A, B = torch.randn(6, 5, generator=g), torch.randn(2, 5, generator=g), torch.randn(6, 2, generator=g)
+    out = lora.fold(W.bfloat16(), A, B, scaling=4.0)
+    assert torch.allclose(out, W.bfloat16().float() + 4.0 * B @ A, atol=1e-6)

@@ -224,6 +224,39 @@ def test_chat_api_on_device():
     assert len(chunks) == 5 and len(chunks[-1][0].split()) == 5 and chunks[-1][1][-1]["type"] == "response"
 
 
+def test_lora_fold_at_load(tmp_path):
+    """Unmerged checkpoint path without peft: fold synthetic LoRA deltas + replaced tensors, compare with the oracle run on the
+    explicitly merged weights (what PeftModel.merge_and_unload would have produced)."""
+    import json
+    import visualcla
+    cfg = O.tiny_config()
+    m = visualcla.VisualCLAModel.from_synthetic(cfg.to_dict(), seed=4, max_batch=2, max_seq=64)
+    w = O.make_weights(cfg, 4)
+    g = torch.Generator().manual_seed(1)
+    r, alpha = 4, 8
+    sd = {}
+    targets = ["text_model.model.layers.0.self_attn.q_proj.weight", "text_model.model.layers.1.mlp.gate_proj.weight",
+               "text_model.model.layers.1.mlp.down_proj.weight", "vision_model.vision_model.encoder.layers.0.self_attn.v_proj.weight",
+               "vision_model.vision_model.encoder.layers.1.mlp.fc2.weight"]
+    for t in targets:
+        out_f, in_f = w[t].shape
+        A, B = torch.randn(r, in_f, generator=g) * 0.05, torch.randn(out_f, r, generator=g) * 0.05
+        base = "base_model.model." + t[: -len(".weight")]
+        sd[base + ".lora_A.weight"], sd[base + ".lora_B.weight"] = A, B
+        w[t] = (w[t] + (alpha / r) * (B @ A)).to(torch.bfloat16).float()
+    newq = (torch.randn(1, cfg.r_queries, cfg.r_hidden, generator=g)).to(torch.bfloat16).float()
+    sd["base_model.model.visual_resampler.query_embeddding"] = newq
+    w["visual_resampler.query_embeddding"] = newq
+    torch.save(sd, tmp_path / "adapter_model.bin")
+    json.dump({"r": r, "lora_alpha": alpha, "fan_in_fan_out": False}, open(tmp_path / "adapter_config.json", "w"))
+    info = visualcla.load_lora(m, str(tmp_path))
+    assert info["folded"] == len(targets) and info["replaced"] == 1
+    px, ids = O.make_inputs(cfg, 2, 10, seed=6)
+    got = m.forward(input_ids=ids.cuda(), pixel_values=px.cuda(), labels=ids.cuda()).logits
+    ref = O.forward_logits(w, cfg, ids, px, image_at_head=True)
+    assert _rel_err(got, ref) <= LOGIT_TOL
+
+
 def test_batch_invariance_row_for_row():
     """DP correctness premise: a sample's tokens do not depend on what else is in the batch."""
     cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=2, t_vocab=2003)
