@@ -103,13 +103,19 @@ int vcla_vision_encode(vcla_ctx* ctx, const void* pixels_dev, int pixel_dtype, i
  *   image_mode     VCLA_TEXT_ONLY / VCLA_IMAGE_AT_HEAD / VCLA_IMAGE_PLACEHOLDER
  *   img_row_dev    int32 (B) device: first row of the image block inside each sequence (index of <img> + 1),
  *                  -1 = no image for this sample; ignored for TEXT_ONLY; for AT_HEAD pass NULL (row 2)
+ *   left_pad_dev   int32 (B) device or NULL: number of LEFT padding tokens per sequence (attention_mask = [0]*p + [1]*(T-p),
+ *                  what HF generate expects for batched prompts of different lengths): pad keys are masked, the KV cache
+ *                  holds only the real tokens.  pos_from_mask != 0: RoPE positions count real tokens from 0
+ *                  (HF generate: position_ids = attention_mask.cumsum(-1) - 1); 0: positions are arange(S) (plain forward(),
+ *                  which the reference calls without position_ids, modeling_visualcla.py:321-328).  Not with IMAGE_AT_HEAD.
  *   logits_all_dev f32 (B,S,V) or NULL   -- VisualCLAModel.forward(...).logits (modeling_visualcla.py:321-328)
  *   last_logits_dev f32 (B,V) or NULL    -- logits of the last position (what generate() samples from)
  *   next_tok_dev   int32 (B) or NULL     -- argmax of last_logits (greedy)
  * Fills the KV cache; sequence length becomes S.  Replaces the splice (modeling_visualcla.py:290-312 /
  * :356-377) + LlamaForCausalLM prefill (HF:models/llama/modeling_llama.py:375-501). */
 int vcla_prefill(vcla_ctx* ctx, const int64_t* ids_dev, int B, int T, int image_mode, const int32_t* img_row_dev,
-                 float* logits_all_dev, float* last_logits_dev, int32_t* next_tok_dev, vcla_stream stream);
+                 const int32_t* left_pad_dev, int pos_from_mask, float* logits_all_dev, float* last_logits_dev,
+                 int32_t* next_tok_dev, vcla_stream stream);
 
 /* One greedy decode step for the B resident sequences: consumes tok_in_dev (int32 (B)), appends its K/V,
  * writes logits (f32 (B,V), optional) and the argmax (int32 (B)).  Captured into a CUDA graph on first use

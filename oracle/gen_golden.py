@@ -140,6 +140,39 @@ def case_resampler_fullwidth(visualcla, seed=3):
     print(f"[golden] resampler_fullwidth: out {tuple(y.shape)} absmax {float(y.abs().max()):.3f}")
 
 
+@torch.no_grad()
+def case_tiny_padded(visualcla, seed=2):
+    """Left-padded batch of different prompt lengths through the reference's generate() (placeholder layout, what the loader
+    configures): HF derives position_ids from the attention mask and masks the pad keys."""
+    from transformers import GenerationConfig
+    cfg = O.tiny_config()
+    w = O.make_weights(cfg, seed)
+    model = build_reference_model(visualcla, cfg, w)
+    s0, s1, s2, s3 = O.special_ids(cfg)
+    B, T, nq, n_new = 3, 14, cfg.r_queries, 6
+    pads = [0, 3, 6]
+    pixels, raw = O.make_inputs(cfg, B, T, seed=1234 + seed)
+    S = T + nq
+    ids = torch.full((B, S), s2, dtype=torch.long)          # <pad>
+    mask = torch.zeros(B, S, dtype=torch.long)
+    for b, p in enumerate(pads):
+        body = torch.cat([raw[b, :2], torch.full((nq,), s3, dtype=torch.long), raw[b, 2:T - p]])   # [bos,<img>,8x<img_token>,</img>,text...]
+        ids[b, S - body.numel():] = body
+        mask[b, S - body.numel():] = 1
+        assert S - body.numel() == p
+    model.image_at_head = False
+    model.tokenizer = types.SimpleNamespace(img_start_token_id=s0, img_end_token_id=s1, img_token_id=s3)
+    gc = GenerationConfig(do_sample=False, max_new_tokens=n_new, eos_token_id=None, pad_token_id=s2, bos_token_id=1,
+                          output_logits=True, return_dict_in_generate=True)
+    gen = model.generate(input_ids=ids, pixel_values=pixels, attention_mask=mask, generation_config=gc)
+    fwd = model(input_ids=ids, pixel_values=pixels, attention_mask=mask, return_dict=True).logits
+    np.savez_compressed(os.path.join(OUT, "tiny_padded.npz"), config=np.array(repr(cfg.to_dict())), seed=np.array(seed),
+                        pixel_values=pixels.numpy(), input_ids=ids.numpy(), attention_mask=mask.numpy(), pads=np.array(pads),
+                        gen_tokens=gen.sequences.numpy(), gen_logits=torch.stack(list(gen.logits), 1).float().numpy(),
+                        forward_logits=fwd.numpy())
+    print(f"[golden] tiny_padded: pads {pads} gen {tuple(gen.sequences.shape)}")
+
+
 def case_host_logic(visualcla):
     """Prompt strings (ref: modeling_utils.py:49-80) and the extra samplers (ref: :250-320) for the host-side tests."""
     import json
@@ -175,6 +208,7 @@ def main():
     case_tiny(visualcla, "tiny_b2_t12", seed=0, batch=2, t_text=12, n_new=8)
     case_tiny(visualcla, "tiny_b3_t7", seed=1, batch=3, t_text=7, n_new=5)
     case_resampler_fullwidth(visualcla)
+    case_tiny_padded(visualcla)
     case_host_logic(visualcla)
 
 

@@ -423,7 +423,7 @@ def rope_tables(cfg: PathConfig, positions: torch.Tensor) -> Tuple[torch.Tensor,
 
 
 def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
-    """x (B,H,S,hd); cos/sin (S,hd).  HF:models/llama/modeling_llama.py:144-170 (rotate_half)."""
+    """x (B,H,S,hd); cos/sin (S,hd) or (B,1,S,hd).  HF:models/llama/modeling_llama.py:144-170 (rotate_half)."""
     h = x.shape[-1] // 2
     rot = torch.cat([-x[..., h:], x[..., :h]], dim=-1)
     return x * cos + rot * sin
@@ -440,16 +440,26 @@ class KVCache:
 
 
 def llama_forward(w, cfg: PathConfig, embeds: torch.Tensor, cache: Optional[KVCache] = None,
-                  last_only: bool = False, weights_bf16: Optional[dict] = None) -> torch.Tensor:
-    """LlamaForCausalLM.forward(inputs_embeds=...) with causal mask and position_ids = arange
+                  last_only: bool = False, weights_bf16: Optional[dict] = None,
+                  left_pad: Optional[torch.Tensor] = None, pos_from_mask: bool = True) -> torch.Tensor:
+    """LlamaForCausalLM.forward(inputs_embeds=...) with causal mask.  Without `left_pad`: position_ids = arange
     (equal-length, unpadded prompts).  HF:models/llama/modeling_llama.py:375-425 (model),
     :303-332 (layer), :251-289 (attention), :173-186 (MLP), :486-487 (lm_head).
-    With a cache: appends K,V (HF:cache_utils.py:119-120) and attends over past+new."""
+    With a cache: appends K,V (HF:cache_utils.py:119-120) and attends over past+new.
+    `left_pad` (B,) = number of left padding tokens per sequence (attention_mask = [0]*p + [1]*(S-p)): pad keys are
+    masked; with pos_from_mask (what generate() does: position_ids = attention_mask.cumsum(-1) - 1,
+    HF:generation/utils.py prepare_inputs_for_generation) real tokens are numbered from 0, otherwise (plain forward(), which
+    the reference calls without position_ids, ref: modeling_visualcla.py:321-328) positions are arange(S)."""
     tp = "text_model.model."
     B, S, T = embeds.shape
     H, hd = cfg.t_heads, cfg.t_head_dim
     past = cache.length if cache is not None else 0
-    cos, sin = rope_tables(cfg, torch.arange(past, past + S))
+    pad = torch.zeros(B, dtype=torch.long) if left_pad is None else left_pad.long()
+    pos = torch.arange(past, past + S)[None, :].expand(B, S)
+    if pos_from_mask:
+        pos = (pos - pad[:, None]).clamp(min=0)
+    cosb, sinb = rope_tables(cfg, pos.reshape(-1))
+    cosb, sinb = cosb.view(B, 1, S, hd), sinb.view(B, 1, S, hd)
     h = embeds.float()
     scale = hd ** -0.5
 
@@ -464,8 +474,8 @@ def llama_forward(w, cfg: PathConfig, embeds: torch.Tensor, cache: Optional[KVCa
         q = (y @ W(lp + "self_attn.q_proj.weight").t()).view(B, S, H, hd).transpose(1, 2)
         k = (y @ W(lp + "self_attn.k_proj.weight").t()).view(B, S, H, hd).transpose(1, 2)
         v = (y @ W(lp + "self_attn.v_proj.weight").t()).view(B, S, H, hd).transpose(1, 2)
-        q = apply_rope(q, cos, sin)
-        k = apply_rope(k, cos, sin)
+        q = apply_rope(q, cosb, sinb)
+        k = apply_rope(k, cosb, sinb)
         if cache is not None:
             if cache.k[i] is not None:
                 k = torch.cat([cache.k[i], k], dim=2)
@@ -473,10 +483,12 @@ def llama_forward(w, cfg: PathConfig, embeds: torch.Tensor, cache: Optional[KVCa
             cache.k[i], cache.v[i] = k, v
         Sk = k.shape[2]
         s = torch.matmul(q, k.transpose(-1, -2)) * scale
-        if S > 1:
-            m = torch.ones(S, Sk, dtype=torch.bool).tril(diagonal=Sk - S)
-            s = s.masked_fill(~m, float("-inf"))
+        visible = torch.ones(S, Sk, dtype=torch.bool).tril(diagonal=Sk - S)[None, None]
+        if left_pad is not None:
+            visible = visible & (torch.arange(Sk)[None, :] >= pad[:, None])[:, None, None, :]
+        s = s.masked_fill(~visible, float("-inf"))
         p = torch.softmax(s, dim=-1)
+        p = torch.nan_to_num(p, nan=0.0)          # fully masked rows (queries inside the padding) produce garbage in HF; zero here
         a = torch.matmul(p, v).transpose(1, 2).reshape(B, S, T)
         h = r + a @ W(lp + "self_attn.o_proj.weight").t()
         r = h
@@ -513,7 +525,7 @@ def forward_logits(w, cfg: PathConfig, input_ids, pixel_values, image_at_head: b
 
 def generate_greedy(w, cfg: PathConfig, input_ids, pixel_values, max_new_tokens: int,
                     image_at_head: bool = True, forced_tokens: Optional[torch.Tensor] = None,
-                    return_logits: bool = True):
+                    return_logits: bool = True, left_pad: Optional[torch.Tensor] = None):
     """VisualCLAModel.generate(do_sample=False, eos disabled): returns ONLY the new tokens
     (ref: modeling_visualcla.py:333-392 -> HF:generation/utils.py:2658-2810, argmax of the
     fp32 copy of the last-position logits :2762,:2793).
@@ -523,7 +535,7 @@ def generate_greedy(w, cfg: PathConfig, input_ids, pixel_values, max_new_tokens:
     img = vision_encode(w, cfg, pixel_values) if pixel_values is not None else None
     x = splice(w, cfg, input_ids, img, image_at_head, s0, s1, s3)
     cache = KVCache(cfg.t_layers)
-    logits = llama_forward(w, cfg, x, cache, last_only=True)[:, -1]
+    logits = llama_forward(w, cfg, x, cache, last_only=True, left_pad=left_pad)[:, -1]
     toks, logs = [], []
     for step in range(max_new_tokens):
         nxt = logits.argmax(-1)
@@ -534,5 +546,5 @@ def generate_greedy(w, cfg: PathConfig, input_ids, pixel_values, max_new_tokens:
             break
         feed = nxt if forced_tokens is None else forced_tokens[:, step]
         e = w["text_model.model.embed_tokens.weight"][feed].float().unsqueeze(1)
-        logits = llama_forward(w, cfg, e, cache, last_only=True)[:, -1]
+        logits = llama_forward(w, cfg, e, cache, last_only=True, left_pad=left_pad)[:, -1]
     return torch.stack(toks, 1), (torch.stack(logs, 1) if return_logits else None)

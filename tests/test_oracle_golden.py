@@ -84,3 +84,39 @@ def test_splice_errors():
     ids = torch.tensor([[1, s0, s3, s3, s1, 5]])     # only 2 placeholders for 8 queries
     with pytest.raises((ValueError, IndexError)):
         O.splice(w, cfg, ids, torch.zeros(1, cfg.r_queries, cfg.t_hidden), False, s0, s1, s3)
+
+
+def _padded_inputs(g, cfg):
+    w = O.make_weights(cfg, int(g["seed"]))
+    px = torch.from_numpy(g["pixel_values"])
+    ids = torch.from_numpy(g["input_ids"])
+    pads = torch.from_numpy(g["pads"])
+    s0, s1, _, s3 = O.special_ids(cfg)
+    img = O.vision_encode(w, cfg, px)
+    x = O.splice(w, cfg, ids, img, False, s0, s1, s3)
+    return w, x, pads
+
+
+def test_left_padded_batch_generate_and_forward(golden_dir):
+    """Left-padded prompts of different lengths (tests/golden/tiny_padded.npz from the reference's generate()/forward())."""
+    g, cfg = _load(golden_dir, "tiny_padded")
+    w, x, pads = _padded_inputs(g, cfg)
+    # forward(): the reference passes no position_ids -> arange positions, pad keys masked; compare only real rows
+    lf = O.llama_forward(w, cfg, x, left_pad=pads, pos_from_mask=False)
+    ref = torch.from_numpy(g["forward_logits"])
+    for b, p in enumerate(pads.tolist()):
+        _close(lf[b, p:], ref[b, p:])
+    # generate(): positions from the mask
+    n = g["gen_tokens"].shape[1]
+    cache = O.KVCache(cfg.t_layers)
+    logits = O.llama_forward(w, cfg, x, cache, last_only=True, left_pad=pads)[:, -1]
+    toks, logs = [], []
+    for step in range(n):
+        nxt = logits.argmax(-1)
+        toks.append(nxt); logs.append(logits)
+        if step == n - 1:
+            break
+        e = w["text_model.model.embed_tokens.weight"][nxt].unsqueeze(1)
+        logits = O.llama_forward(w, cfg, e, cache, last_only=True, left_pad=pads)[:, -1]
+    assert np.array_equal(torch.stack(toks, 1).numpy(), g["gen_tokens"])
+    _close(torch.stack(logs, 1), g["gen_logits"])

@@ -224,6 +224,43 @@ def test_chat_api_on_device():
     assert len(chunks) == 5 and len(chunks[-1][0].split()) == 5 and chunks[-1][1][-1]["type"] == "response"
 
 
+def test_left_padded_batch_against_reference_golden(golden_dir):
+    """Prompts of different lengths, LEFT padded (HF batching): tokens/logits vs the reference's generate() and forward()
+    (tests/golden/tiny_padded.npz), and each padded sequence must equal the same sequence run alone without padding."""
+    g, cfg = _load_golden(golden_dir, "tiny_padded")
+    m = _model(cfg, int(g["seed"]), 4, 96)
+    s0, s1, s2, s3 = O.special_ids(cfg)
+    m.image_at_head = False
+    m.tokenizer = types.SimpleNamespace(img_start_token_id=s0, img_end_token_id=s1, img_token_id=s3)
+    px = torch.from_numpy(g["pixel_values"]).cuda()
+    ids = torch.from_numpy(g["input_ids"]).cuda()
+    mask = torch.from_numpy(g["attention_mask"]).cuda()
+    pads = g["pads"].tolist()
+    n = g["gen_tokens"].shape[1]
+    kw = dict(do_sample=False, max_new_tokens=n, eos_token_id=None, pad_token_id=s2)
+    res = m.generate(input_ids=ids, pixel_values=px, attention_mask=mask, output_logits=True, return_dict_in_generate=True, **kw)
+    glog = torch.from_numpy(g["gen_logits"])
+    scale = glog.abs().max().item()
+    e0 = (res.logits[0].cpu() - glog[:, 0]).abs().max().item() / scale
+    assert e0 <= LOGIT_TOL, f"prefill-step logits rel err {e0:.3e}"
+    nbad, ndec, ntot = _margin_ok_tokens(res.sequences, torch.from_numpy(g["gen_tokens"]), glog, LOGIT_TOL * scale, free_running=True)
+    assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
+    # forward(): arange positions, pad keys masked; only real rows are defined
+    fwd = m.forward(input_ids=ids, pixel_values=px, attention_mask=mask).logits.cpu()
+    ref = torch.from_numpy(g["forward_logits"])
+    for b, p in enumerate(pads):
+        assert _rel_err(fwd[b, p:], ref[b, p:]) <= LOGIT_TOL
+    # padding invariance on the device: sequence b alone (unpadded) generates the same tokens as inside the padded batch
+    fast = m.generate(input_ids=ids, pixel_values=px, attention_mask=mask, **kw)
+    assert torch.equal(fast, res.sequences)
+    for b, p in enumerate(pads):
+        alone = m.generate(input_ids=ids[b:b + 1, p:], pixel_values=px[b:b + 1], **kw)
+        assert torch.equal(alone[0], fast[b]), f"sequence {b} (pad {p}) differs from its unpadded run"
+    with pytest.raises(NotImplementedError):
+        bad = mask.clone(); bad[0, -1] = 0
+        m.generate(input_ids=ids, pixel_values=px, attention_mask=bad, **kw)
+
+
 def test_lora_fold_at_load(tmp_path):
     """Unmerged checkpoint path without peft: fold synthetic LoRA deltas + replaced tensors, compare with the oracle run on the
     explicitly merged weights (what PeftModel.merge_and_unload would have produced)."""

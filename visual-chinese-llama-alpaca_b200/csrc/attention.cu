@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   const int Sk = c.n0 + c.n1;
   const int off = Sk - c.Sq;  // causal: kv j visible to query i iff j <= i + off
   TraceScope trace(3);
+  const int kv0 = c.kv_start ? __ldg(c.kv_start + b) : 0;   // left padding: keys before kv0 are invisible
 
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   if (c.causal) kv_end = min(Sk, q0 + BQ + off);
   const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;  // the two query rows this thread owns
 
-  for (int j0 = 0; j0 < kv_end; j0 += BKV) {
+  for (int j0 = (kv0 / BKV) * BKV; j0 < kv_end; j0 += BKV) {
     __syncthreads();  // previous tile fully consumed
     for (int i = tid; i < BKV * CHUNKS; i += 128) {
       int r = i / CHUNKS, ch = i % CHUNKS;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
       for (int e = 0; e < 4; ++e) {
         int j = j0 + nt * 8 + (lane & 3) * 2 + (e & 1);
         int qi = (e < 2) ? r0 : r1;
-        bool vis = (j < Sk) && (!c.causal || j <= qi + off);
+        bool vis = (j < Sk) && (j >= kv0) && (!c.causal || j <= qi + off);
         float v = vis ? s[nt][e] * sl2 : -INFINITY;
         s[nt][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);

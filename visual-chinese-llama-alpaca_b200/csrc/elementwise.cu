@@ -316,17 +316,20 @@ int rope_init(int max_pos, int head_dim, float theta) {
 // One CTA per token; each thread owns 8 consecutive rotary pairs of one head: 128-bit loads/stores throughout.
 __global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int HD, const float* __restrict__ rc, const float* __restrict__ rs,
                                       bf16* __restrict__ kv_pages, const int32_t* __restrict__ page_table, int pages_per_seq,
-                                      int page_tokens, const int32_t* __restrict__ seq_base) {
+                                      int page_tokens, const int32_t* __restrict__ left_pad, int pos_from_mask) {
   TraceScope trace(7);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
   trace.dep();
   const int s = blockIdx.x, b = blockIdx.y;
   const int T = H * HD, half = HD / 2, groups = half / 8;
-  const int pos = (seq_base ? seq_base[b] : 0) + s;
+  const int pad = left_pad ? left_pad[b] : 0;
+  if (s < pad) return;                                 // padding row: not rotated, not cached, masked in attention
+  const int cpos = s - pad;                            // index inside the (compact) KV cache
+  const int pos = pos_from_mask ? cpos : s;            // rotary position
   bf16* row = qkv + ((size_t)b * S + s) * 3 * T;
-  const int page = page_table[(size_t)b * pages_per_seq + pos / page_tokens];
-  const int slot = pos % page_tokens;
+  const int page = page_table[(size_t)b * pages_per_seq + cpos / page_tokens];
+  const int slot = cpos % page_tokens;
   for (int idx = threadIdx.x; idx < H * groups; idx += blockDim.x) {
     const int h = idx / groups, i = (idx % groups) * 8;
     float cs[8], sn[8];
@@ -362,11 +365,11 @@ __global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int 
   }
 }
 int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table, int pages_per_seq,
-                   int page_tokens, const int32_t* seq_base, cudaStream_t st) {
+                   int page_tokens, const int32_t* left_pad, int pos_from_mask, cudaStream_t st) {
   (void)theta;
   if (!g_rope_cos) { set_error("rope table not initialised"); return -1; }
   VCLA_LAUNCH(rope_and_cache_kernel, dim3(S, B), dim3(256), 0, st, qkv, S, H, HD, (const float*)g_rope_cos, (const float*)g_rope_sin,
-              kv_pages, page_table, pages_per_seq, page_tokens, seq_base);
+              kv_pages, page_table, pages_per_seq, page_tokens, left_pad, pos_from_mask);
   return 0;
 }
 
@@ -548,6 +551,17 @@ __global__ void advance_seq_kernel(int32_t* seq_len, int B, int by, int32_t* ste
 }
 int advance_seq(int32_t* seq_len, int B, int by, int32_t* step_idx, cudaStream_t st) {
   VCLA_LAUNCH(advance_seq_kernel, dim3((B + 63) / 64), dim3(64), 0, st, seq_len, B, by, step_idx);
+  return 0;
+}
+
+__global__ void advance_seq_padded_kernel(int32_t* seq_len, int B, int S, const int32_t* left_pad, int32_t* step_idx) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) seq_len[b] += S - (left_pad ? left_pad[b] : 0);
+  if (step_idx != nullptr && b == 0) *step_idx += 1;
+}
+int advance_seq_padded(int32_t* seq_len, int B, int S, const int32_t* left_pad, int32_t* step_idx, cudaStream_t st) {
+  advance_seq_padded_kernel<<<(B + 63) / 64, 64, 0, st>>>(seq_len, B, S, left_pad, step_idx);
+  VCLA_CUDA_OK(cudaGetLastError());
   return 0;
 }
 

@@ -629,8 +629,8 @@ static int lm_head_last(vcla_ctx* c, int B, float* logits_dev, int32_t* tok_dev,
   return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, c->tok_hist, c->step_idx, nullptr, st);
 }
 
-int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, float* logits_all,
-                 float* last_logits, int32_t* next_tok, vcla_stream stream) {
+int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, const int32_t* left_pad,
+                 int pos_from_mask, float* logits_all, float* last_logits, int32_t* next_tok, vcla_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const vcla_config& g = c->cfg;
   const int nq = g.r_queries, TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
@@ -639,6 +639,7 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
   if ((long)B * S > g.max_prefill_tokens) { set_error("prefill: %d x %d tokens exceed max_prefill_tokens %d", B, S, g.max_prefill_tokens); return -1; }
   if (S > g.max_seq) { set_error("prefill: sequence %d exceeds max_seq %d", S, g.max_seq); return -1; }
   if (image_mode == VCLA_IMAGE_AT_HEAD && T < 2) { set_error("prefill: image_at_head needs >= 2 text tokens"); return -1; }
+  if (image_mode == VCLA_IMAGE_AT_HEAD && left_pad != nullptr) { set_error("prefill: left padding is not defined for the image_at_head layout"); return -1; }
   const int rows = B * S;
   if (vcla_reset(c, stream)) return -1;
   count(c); if (embed_tokens(ids, B, T, S, TH, c->embed, g.t_vocab, image_mode == VCLA_IMAGE_AT_HEAD ? 1 : 0, nq, c->resid, st)) return -1;
@@ -651,9 +652,9 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
     const TextLayer& L = c->tl[i];
     count(c); if (rmsnorm(c->resid, rows, TH, L.ln1, g.t_eps, c->xn, st)) return -1;
     if (gemm_bf16(c, c->xn, rows, TH, TH, L.wqkv, 3 * TH, TH, nullptr, ACT_NONE, c->qkv, 3 * TH, st)) return -1;
-    count(c); if (rope_and_cache(c->qkv, B, S, H, 128, g.rope_theta, L.kv, c->page_table, c->pages_per_seq, c->page_tokens, nullptr, st)) return -1;
+    count(c); if (rope_and_cache(c->qkv, B, S, H, 128, g.rope_theta, L.kv, c->page_table, c->pages_per_seq, c->page_tokens, left_pad, pos_from_mask, st)) return -1;
     AttnCall a; a.q = c->qkv; a.q_stride = 3 * TH; a.k0 = c->qkv + TH; a.v0 = c->qkv + 2 * TH; a.kv0_stride = 3 * TH; a.n0 = S;
-    a.out = c->attn; a.o_stride = TH; a.B = B; a.H = H; a.Sq = S; a.HD = 128; a.scale = scale; a.causal = 1;
+    a.out = c->attn; a.o_stride = TH; a.B = B; a.H = H; a.Sq = S; a.HD = 128; a.scale = scale; a.causal = 1; a.kv_start = left_pad;
     count(c); if (attention_prefill(a, st)) return -1;
     if (gemm_f32(c, c->attn, rows, TH, TH, L.wo, TH, TH, nullptr, 1, c->resid, TH, st)) return -1;
     count(c); if (rmsnorm(c->resid, rows, TH, L.ln2, g.t_eps, c->xn, st)) return -1;
@@ -669,7 +670,7 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
   }
   count(c); if (gather_last_rows(c->resid, B, S, TH, c->d_resid, st)) return -1;
   if (lm_head_last(c, B, last_logits, next_tok, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, S, c->step_idx, st)) return -1;
+  count(c); if (left_pad ? advance_seq_padded(c->seq_len, B, S, left_pad, c->step_idx, st) : advance_seq(c->seq_len, B, S, c->step_idx, st)) return -1;
   return 0;
 }
 

@@ -98,6 +98,7 @@ struct AttnCall {
   int B = 0, H = 0, Sq = 0, HD = 0;
   float scale = 1.f;
   int causal = 0;
+  const int32_t* kv_start = nullptr;   // [B] first visible kv index per sequence (left padding); null: 0
 };
 int attention_prefill(const AttnCall& c, cudaStream_t st);
 
@@ -139,8 +140,11 @@ int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vo
 // copy the projected image rows (B, nq, D) fp32 into the residual stream at per-sample row offsets
 int scatter_image_rows(const float* img, int B, int nq, int D, const int32_t* row_start, int S, float* dst, cudaStream_t st);
 // prefill: RoPE q,k in place in the fused qkv buffer [B*S, 3T] and append k,v to the paged cache
+// left_pad[b] (nullable): rows s < left_pad[b] are padding (skipped); the cache index of row s is s - left_pad[b]; the RoPE
+// position is s - left_pad[b] when pos_from_mask (HF generate) else s (plain forward without position_ids)
 int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table,
-                   int pages_per_seq, int page_tokens, const int32_t* seq_base, cudaStream_t st);
+                   int pages_per_seq, int page_tokens, const int32_t* left_pad, int pos_from_mask, cudaStream_t st);
+int advance_seq_padded(int32_t* seq_len, int B, int S, const int32_t* left_pad, int32_t* step_idx, cudaStream_t st);
 int gather_last_rows(const float* hidden, int B, int S, int D, float* dst, cudaStream_t st);
 
 // decode consumers of split-K partials

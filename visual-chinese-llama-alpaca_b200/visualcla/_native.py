@@ -44,7 +44,7 @@ _SIGNATURES = [
     ("vcla_init_synthetic", C.c_int, [_P, C.c_uint32, _P]),
     ("vcla_reset", C.c_int, [_P, _P]),
     ("vcla_vision_encode", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
-    ("vcla_prefill", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    ("vcla_prefill", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     ("vcla_decode_step", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     ("vcla_read_history", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     ("vcla_kernel_launches", C.c_int64, [_P, C.c_int]),

@@ -129,7 +129,7 @@ class Engine:
         return out
 
     def prefill(self, input_ids: torch.Tensor, image_mode: int, img_rows: Optional[torch.Tensor] = None,
-                all_logits: bool = False, last_logits: bool = True):
+                all_logits: bool = False, last_logits: bool = True, left_pad: Optional[torch.Tensor] = None, pos_from_mask: bool = True):
         ids = input_ids.to(self.device, dtype=torch.int64).contiguous()
         B, T = ids.shape
         S = T + self.nq if image_mode == N.IMAGE_AT_HEAD else T
@@ -137,9 +137,10 @@ class Engine:
         ll = torch.empty(B, self.vocab, dtype=torch.float32, device=self.device) if last_logits else None
         tok = torch.empty(B, dtype=torch.int32, device=self.device)
         rows = None if img_rows is None else img_rows.to(self.device, dtype=torch.int32).contiguous()
+        pad = None if left_pad is None else left_pad.to(self.device, dtype=torch.int32).contiguous()
         with torch.cuda.device(self.device):
-            N.check(self.lib.vcla_prefill(self._ctx, N.ptr(ids), B, T, image_mode, N.ptr(rows), N.ptr(la), N.ptr(ll), N.ptr(tok),
-                                          self._stream()), "vcla_prefill")
+            N.check(self.lib.vcla_prefill(self._ctx, N.ptr(ids), B, T, image_mode, N.ptr(rows), N.ptr(pad), 1 if pos_from_mask else 0,
+                                          N.ptr(la), N.ptr(ll), N.ptr(tok), self._stream()), "vcla_prefill")
         return ll, tok, la
 
     def decode_step(self, tok_in: torch.Tensor, tok_out: torch.Tensor, logits: Optional[torch.Tensor] = None, use_graph: bool = True):

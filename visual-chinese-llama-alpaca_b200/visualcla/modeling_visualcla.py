@@ -307,11 +307,23 @@ class VisualCLAModel:
             rows.append(p + 1)
         return N.IMAGE_PLACEHOLDER, torch.tensor(rows, dtype=torch.int32)
 
-    @staticmethod
-    def _check_mask(attention_mask):
-        if attention_mask is not None and not bool((attention_mask != 0).all()):
-            raise NotImplementedError("padded batches (attention_mask with zeros) are a 'next' row of the B200 path "
-                                      "(SURVEY 8f-3); use equal-length prompts")
+    def _left_pad(self, attention_mask, image_mode):
+        """attention_mask -> per-sequence left-padding counts (or None).  HF batches prompts of different lengths by LEFT
+        padding; any other mask shape is rejected."""
+        if attention_mask is None or bool((attention_mask != 0).all()):
+            return None
+        m = (attention_mask != 0).to("cpu")
+        pads = (~m).sum(1)
+        T = m.shape[1]
+        expect = torch.arange(T)[None, :] >= pads[:, None]
+        if not torch.equal(m, expect):
+            raise NotImplementedError("only left padding (attention_mask = [0]*p + [1]*(T-p)) is supported on the B200 path")
+        if bool((pads >= T).any()):
+            raise ValueError("attention_mask masks a whole sequence")
+        if image_mode == N.IMAGE_AT_HEAD:
+            raise NotImplementedError("padded batches need the placeholder layout (image_at_head=False): the reference's at-head splice "
+                                      "ignores the mask (ref modeling_visualcla.py:291)")
+        return pads.to(torch.int32)
 
     # ---- forward: logits for every position (ref :264-330) ---------------------------------------
     @torch.no_grad()
@@ -320,15 +332,15 @@ class VisualCLAModel:
         from transformers.modeling_outputs import CausalLMOutputWithPast
         if past_key_values is not None:
             raise NotImplementedError("forward(past_key_values=...) is not supported; use generate()")
-        self._check_mask(attention_mask)
         mode, rows = self._image_layout(input_ids, pixel_values)
+        pads = self._left_pad(attention_mask, mode)
         eng = self._engine
         if mode != N.TEXT_ONLY:
             if mode == N.IMAGE_AT_HEAD and labels is None:
                 # ref quirk (:313-315): labels[:, [0]] is indexed unconditionally in this layout
                 raise TypeError("'NoneType' object is not subscriptable (labels are required with image_at_head=True)")
             eng.vision_encode(pixel_values)
-        _, _, logits = eng.prefill(input_ids, mode, rows, all_logits=True, last_logits=False)
+        _, _, logits = eng.prefill(input_ids, mode, rows, all_logits=True, last_logits=False, left_pad=pads, pos_from_mask=False)
         loss = None
         if labels is not None:
             lab = labels.to(logits.device)
@@ -367,7 +379,6 @@ class VisualCLAModel:
     def generate(self, input_ids=None, pixel_values=None, attention_mask=None, generation_config=None,
                  logits_processor=None, stopping_criteria=None, prefix_allowed_tokens_fn=None, synced_gpus=False, **kwargs):
         gc = self._resolve_generation_config(generation_config, kwargs)
-        self._check_mask(attention_mask)
         if prefix_allowed_tokens_fn is not None:
             raise NotImplementedError("prefix_allowed_tokens_fn is not supported on the B200 path")
         eng = self._engine
@@ -376,7 +387,8 @@ class VisualCLAModel:
             outs = []
             for s in range(0, B, eng.max_batch):
                 sl = slice(s, s + eng.max_batch)
-                outs.append(self.generate(input_ids[sl], None if pixel_values is None else pixel_values[sl], None,
+                outs.append(self.generate(input_ids[sl], None if pixel_values is None else pixel_values[sl],
+                                          None if attention_mask is None else attention_mask[sl],
                                           gc, logits_processor, stopping_criteria, None, synced_gpus))
             width = max(o.shape[1] for o in outs)
             pad = gc.pad_token_id if gc.pad_token_id is not None else 0
@@ -384,6 +396,7 @@ class VisualCLAModel:
             return torch.cat(outs, 0)
 
         mode, rows = self._image_layout(input_ids, pixel_values)
+        pads = self._left_pad(attention_mask, mode)
         S = input_ids.shape[1] + (eng.nq if mode == N.IMAGE_AT_HEAD else 0)
         max_new = gc.max_new_tokens if gc.max_new_tokens is not None else max(int(gc.max_length or 20), 1)
         min_new = int(getattr(gc, "min_new_tokens", 0) or 0)
@@ -411,7 +424,7 @@ class VisualCLAModel:
         out = torch.full((B, max_new), pad, dtype=torch.int64, device=dev)
         all_logits: List[torch.Tensor] = []
 
-        last, first_tok, _ = eng.prefill(input_ids, mode, rows, all_logits=False, last_logits=need_logits)
+        last, first_tok, _ = eng.prefill(input_ids, mode, rows, all_logits=False, last_logits=need_logits, left_pad=pads, pos_from_mask=True)
         if not need_logits and not eos and not crit:
             # pure greedy, fixed length: graph replays only; tokens come from the device-side history the graph appends to
             tok.copy_(first_tok)
