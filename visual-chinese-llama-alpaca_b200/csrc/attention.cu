@@ -211,14 +211,17 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
 // decode (hd = 128): grid (kv_splits, H, B), 128 threads
 // =================================================================================================
 constexpr int kDecWarps = 8;        // 256 threads
-constexpr int kDecStages = 3;       // KV pages in flight per CTA (3 x 32 KB at 64 tokens/page -> 2 CTAs per SM)
+#ifndef VCLA_DEC_STAGES
+#define VCLA_DEC_STAGES 2
+#endif
+constexpr int kDecStages = VCLA_DEC_STAGES;   // KV pages in flight per CTA: 2 x 32 KB at 64 tokens/page -> 3 CTAs per SM (3 stages -> 2 CTAs)
 constexpr int kDecMaxPT = 64;       // page_tokens supported by the smem ring
 
 // One CTA per (kv split, head, sequence).  The cached K/V rows of a head are contiguous per page (page_tokens x 128 bf16 =
 // 16 KB), so whole pages are streamed with TMA bulk copies (cp.async.bulk, mbarrier completion) into a 3-stage shared-memory
 // ring and the dot products / PV accumulation run out of shared memory: the kernel is bandwidth- instead of latency-bound
 // (the register-prefetch version had one DRAM round trip per 32 tokens per CTA).
-__global__ void __launch_bounds__(kDecWarps * 32, 2) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+__global__ void __launch_bounds__(kDecWarps * 32, kDecStages == 2 ? 3 : 2) attn_decode_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
                                                                      const float* __restrict__ rope_sin) {
   constexpr int HD = 128;
   extern __shared__ __align__(128) uint8_t dsm[];      // [kDecStages][2][PT][HD] bf16
