@@ -81,6 +81,7 @@ def test_tiny_against_reference_golden(golden_dir, name):
         assert e <= STAGE_TOL, f"{st}: rel err {e:.3e}"
     e = _rel_err(out.logits, g["logits_at_head"])
     assert e <= LOGIT_TOL, f"logits_at_head rel err {e:.3e}"
+    assert _rel_err(m.embed_images(px), g["projector_out"]) <= STAGE_TOL      # tg-webui entry point (embed_images)
     # placeholder layout (what get_model_and_tokenizer_and_processor configures)
     s0, s1, _, s3 = O.special_ids(cfg)
     m.image_at_head = False

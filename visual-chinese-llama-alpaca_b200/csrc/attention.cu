@@ -212,9 +212,9 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
 // =================================================================================================
 constexpr int kDecWarps = 8;        // 256 threads
 #ifndef VCLA_DEC_STAGES
-#define VCLA_DEC_STAGES 2
+#define VCLA_DEC_STAGES 3
 #endif
-constexpr int kDecStages = VCLA_DEC_STAGES;   // KV pages in flight per CTA: 2 x 32 KB at 64 tokens/page -> 3 CTAs per SM (3 stages -> 2 CTAs)
+constexpr int kDecStages = VCLA_DEC_STAGES;   // KV pages in flight per CTA: 3 x 32 KB at 64 tokens/page -> 2 CTAs per SM (2 stages / 3 CTAs measured slower: B=32 37 vs 34 us per layer)
 constexpr int kDecMaxPT = 64;       // page_tokens supported by the smem ring
 
 // One CTA per (kv split, head, sequence).  The cached K/V rows of a head are contiguous per page (page_tokens x 128 bf16 =

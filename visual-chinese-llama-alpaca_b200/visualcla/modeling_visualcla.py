@@ -283,6 +283,12 @@ class VisualCLAModel:
             json.dump(self.config.vision_config, f)
         self.config.save_pretrained(output_dir)
 
+    @torch.no_grad()
+    def embed_images(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """pixels (N,3,I,I) -> image embeddings (N, num_query_tokens, text_hidden): the tg-webui pipeline's entry point
+        (ref: scripts/inference/text_generation_webui/visualcla/visualcla.py:116-129)."""
+        return self._engine.vision_encode(pixel_values, return_embeds=True)
+
     # ---- prompt assembly (host side of ref :290-312 / :356-377) -----------------------------------
     def _image_layout(self, input_ids: torch.Tensor, pixel_values):
         """-> (image_mode, img_rows or None).  Replicates the reference's per-sample checks for the placeholder layout."""
