@@ -176,6 +176,18 @@ def test_fused_decode_schedule_matches(monkeypatch):
     assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
 
 
+def test_persistent_decode_attention(monkeypatch):
+    """The warp-specialised persistent decode-attention kernel (used when sequences x heads outnumber the resident CTAs, e.g.
+    batch 32 x 32 heads) forced onto a small problem with 5 CTAs, so every CTA walks several (sequence, head) items and the
+    KV ring wraps across items."""
+    monkeypatch.setenv("VCLA_ATTN_PERSISTENT", "2")
+    monkeypatch.setenv("VCLA_ATTN_PERSISTENT_GRID", "5")
+    cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=1024, t_heads=8, t_ffn=1408, t_layers=2, t_vocab=2003)
+    m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 17, 4, 150, 20, 512)
+    assert err <= LOGIT_TOL, f"teacher-forced logits rel err {err:.3e}"
+    assert nbad == 0, f"{nbad} decisive tokens differ ({ndec}/{ntot} decisive)"
+
+
 def test_chat_api_on_device():
     """The reference's chat()/chat_in_stream() entry points (ref: modeling_utils.py:143-247) drive the CUDA path end to end
     (stub tokenizer / image processor: no tokenizer files exist offline)."""

@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace vcla {
 
 // =================================================================================================
@@ -458,6 +460,204 @@ __global__ void __launch_bounds__(kDecWarps * 32, kDecStages == 2 ? 3 : 2) attn_
   trace.done();
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Persistent variant for large batches (more (sequence, head) items than resident CTAs, kv_splits == 1): each CTA loops over
+// items; a dedicated producer warp streams the KV pages of item i+1 into the ring while the 8 consumer warps are still in the
+// reduction / epilogue of item i, so the fixed per-item latency chain (seq_len -> page table -> TMA -> q reduce -> combine)
+// is paid once per CTA instead of once per wave (B=32: 3.5 waves of one-shot CTAs).
+// ------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persistent_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+                                                                                       const float* __restrict__ rope_sin, int n_items) {
+  constexpr int HD = 128;
+  constexpr int NC = kDecWarps * 32;                    // consumer threads
+  extern __shared__ __align__(128) uint8_t dsm[];      // [kDecStages][2][PT][HD] bf16
+  __shared__ __align__(8) uint64_t s_full[kDecStages];
+  __shared__ __align__(8) uint64_t s_empty[kDecStages];
+  __shared__ float s_q[HD];
+  __shared__ float s_k[HD];
+  __shared__ float s_v[HD];
+  __shared__ float s_acc[kDecWarps][HD];
+  __shared__ float s_m[kDecWarps], s_l[kDecWarps];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = c.H * HD, PT = c.page_tokens;
+  const uint32_t stage_bytes = (uint32_t)PT * HD * 2 * 2;
+  TraceScope trace(4);
+  if (tid == 0) {
+    for (int s = 0; s < kDecStages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), kDecWarps); }
+    fence_barrier_init();
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.dep();
+  __syncthreads();
+
+  if (warp == kDecWarps) {
+    // ===================== producer warp =====================
+    if (lane == 0) {
+      uint32_t n = 0;                                   // pages issued so far (ring position)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / c.H, h = item % c.H;
+        const int L = c.seq_len[b];
+        const int npages = (L + PT - 1) / PT;
+        for (int i = 0; i < npages; ++i, ++n) {
+          const int stage = n % kDecStages;
+          mbar_wait(smem_u32(&s_empty[stage]), ((n / kDecStages) & 1u) ^ 1u);
+          const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + i);
+          const int ntok = min(PT, L - i * PT);
+          const uint32_t bytes = (uint32_t)ntok * HD * 2;
+          const uint32_t bar = smem_u32(&s_full[stage]);
+          const uint32_t dst = smem_u32(dsm) + stage * stage_bytes;
+          const bf16* ksrc = c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * PT) * HD;
+          const bf16* vsrc = c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * PT) * HD;
+          mbar_arrive_expect_tx(bar, 2 * bytes);
+          bulk_load_1d(dst, ksrc, bytes, bar);
+          bulk_load_1d(dst + (uint32_t)PT * HD * 2, vsrc, bytes, bar);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumer warps (named barrier 1, NC threads) =====================
+  const int grp = lane >> 3, sub = lane & 7;
+  const uint32_t gmask = 0xffu << (grp * 8);
+  uint32_t n = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int b = item / c.H, h = item % c.H;
+    const int L = c.seq_len[b];
+    const int npages = (L + PT - 1) / PT;
+    // ---- q (and the new token's k, v): reduce split-K partials, deferred norm scale, RoPE, append to the cache
+    {
+      const int d = tid & (HD - 1);
+      float qv = 0.f, kv = 0.f, vv = 0.f;
+      if (tid < HD) {
+        for (int s = 0; s < c.splits; ++s) {
+          const float* row = c.qkv_partial + ((size_t)s * c.ws_rows + b) * (size_t)(3 * T);
+          qv += __ldcg(row + h * HD + d);
+          kv += __ldcg(row + T + h * HD + d);
+          vv += __ldcg(row + 2 * T + h * HD + d);
+        }
+        if (c.rstd != nullptr) { const float rs = __ldcg(c.rstd + b); qv *= rs; kv *= rs; vv *= rs; }
+        s_q[d] = qv; s_k[d] = kv; s_v[d] = vv;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+      float qr = 0.f, kr = 0.f;
+      if (tid < HD) {
+        const float cs = rope_cos[(size_t)L * (HD / 2) + (d & 63)], sn = rope_sin[(size_t)L * (HD / 2) + (d & 63)];
+        const float qp = (d < 64) ? -s_q[d + 64] : s_q[d - 64];
+        const float kp = (d < 64) ? -s_k[d + 64] : s_k[d - 64];
+        qr = (qv * cs + qp * sn) * c.scale;
+        kr = kv * cs + kp * sn;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+      if (tid < HD) {
+        s_q[d] = qr;
+        const bf16 kb = __float2bfloat16(kr), vb = __float2bfloat16(vv);
+        s_k[d] = __bfloat162float(kb);
+        s_v[d] = __bfloat162float(vb);
+        const int page = c.page_table[(size_t)b * c.pages_per_seq + L / PT];
+        const int slot = L % PT;
+        c.kv_pages[((((size_t)page * 2 + 0) * c.H + h) * PT + slot) * HD + d] = kb;
+        c.kv_pages[((((size_t)page * 2 + 1) * c.H + h) * PT + slot) * HD + d] = vb;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    }
+    float qreg[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { qreg[i] = s_q[sub * 8 + i]; qreg[8 + i] = s_q[64 + sub * 8 + i]; }
+    float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int i = 0; i < npages; ++i, ++n) {
+      const int stage = n % kDecStages;
+      mbar_wait(smem_u32(&s_full[stage]), (n / kDecStages) & 1u);
+      const int ntok = min(PT, L - i * PT);
+      const uint8_t* kbase = dsm + (size_t)stage * stage_bytes;
+      const uint8_t* vbase = kbase + (size_t)PT * HD * 2;
+      for (int tk = warp * 4 + grp; tk < ntok; tk += kDecWarps * 4) {
+        const uint4 k0 = *reinterpret_cast<const uint4*>(kbase + (size_t)tk * HD * 2 + sub * 16);
+        const uint4 k1 = *reinterpret_cast<const uint4*>(kbase + (size_t)tk * HD * 2 + 128 + sub * 16);
+        const uint4 v0 = *reinterpret_cast<const uint4*>(vbase + (size_t)tk * HD * 2 + sub * 16);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(vbase + (size_t)tk * HD * 2 + 128 + sub * 16);
+        const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+        const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float sc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float2 kf = unpack_bf16x2(kw[j]); sc += qreg[2 * j] * kf.x + qreg[2 * j + 1] * kf.y; }
+        sc += __shfl_xor_sync(gmask, sc, 1);
+        sc += __shfl_xor_sync(gmask, sc, 2);
+        sc += __shfl_xor_sync(gmask, sc, 4);
+        const float mn = fmaxf(m, sc);
+        const float cr = __expf(m - mn), p = __expf(sc - mn);
+        m = mn;
+        l = l * cr + p;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 vf = unpack_bf16x2(vw[j]);
+          acc[2 * j] = acc[2 * j] * cr + p * vf.x;
+          acc[2 * j + 1] = acc[2 * j + 1] * cr + p * vf.y;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));     // this warp is done with the stage
+    }
+    __syncwarp();
+    if (warp == 0 && grp == 0) {                                  // the new token, from smem
+      float sc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sc += qreg[i] * s_k[sub * 8 + i] + qreg[8 + i] * s_k[64 + sub * 8 + i];
+      sc += __shfl_xor_sync(0x000000ffu, sc, 1);
+      sc += __shfl_xor_sync(0x000000ffu, sc, 2);
+      sc += __shfl_xor_sync(0x000000ffu, sc, 4);
+      const float mn = fmaxf(m, sc);
+      const float cr = __expf(m - mn), p = __expf(sc - mn);
+      m = mn;
+      l = l * cr + p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] = acc[i] * cr + p * s_v[sub * 8 + i];
+        acc[8 + i] = acc[8 + i] * cr + p * s_v[64 + sub * 8 + i];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+      const float mn = fmaxf(m, m2);
+      const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn), c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+      l = l * c1 + l2 * c2;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
+        acc[i] = acc[i] * c1 + a2 * c2;
+      }
+      m = mn;
+    }
+    if (grp == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s_acc[warp][sub * 8 + i] = acc[i]; s_acc[warp][64 + sub * 8 + i] = acc[8 + i]; }
+      if (sub == 0) { s_m[warp] = m; s_l[warp] = l; }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    if (tid < HD) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kDecWarps; ++w) M = fmaxf(M, s_m[w]);
+      float Lsum = 0.f, O = 0.f;
+#pragma unroll
+      for (int w = 0; w < kDecWarps; ++w) {
+        const float cw = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - M);
+        Lsum += s_l[w] * cw;
+        O += s_acc[w][tid] * cw;
+      }
+      c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(O / Lsum);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");          // s_q / s_acc are reused by the next item
+  }
+  trace.done();
+}
+
 VCLA_DEFINE_TRACE_SETTER(trace_set_attention)
 
 // rope table owned by elementwise.cu
@@ -468,6 +668,7 @@ int attention_decode_init() {
   static bool done = false;
   if (done) return 0;
   VCLA_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecStages * kDecMaxPT * 128 * 2 * 2));
+  VCLA_CUDA_OK(cudaFuncSetAttribute(attn_decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecStages * kDecMaxPT * 128 * 2 * 2));
   done = true;
   return 0;
 }
@@ -484,6 +685,20 @@ int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   int na = 0;
   if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   cfg.attrs = attr; cfg.numAttrs = na;
+  const int n_items = c.B * c.H;
+  int slots = 2 * num_sms();
+  // VCLA_ATTN_PERSISTENT: 0 = never, 1 (default) = when items outnumber the resident CTAs, 2 = whenever kv_splits == 1 (tests);
+  // VCLA_ATTN_PERSISTENT_GRID caps the persistent grid (tests: several items per CTA on small problems)
+  const char* pe = getenv("VCLA_ATTN_PERSISTENT");
+  const int pmode = pe ? atoi(pe) : 1;
+  if (const char* ge = getenv("VCLA_ATTN_PERSISTENT_GRID")) { const int g2 = atoi(ge); if (g2 > 0 && g2 < slots) slots = g2; }
+  if (c.kv_splits == 1 && ((pmode == 1 && n_items > slots) || pmode == 2)) {
+    // more (sequence, head) items than resident CTAs: persistent, warp-specialised variant
+    cfg.gridDim = dim3(n_items < slots ? n_items : slots);
+    cfg.blockDim = dim3((kDecWarps + 1) * 32);
+    VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_persistent_kernel, c, rope_cos_table(), rope_sin_table(), n_items));
+    return 0;
+  }
   VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_kernel, c, rope_cos_table(), rope_sin_table()));
   return 0;
 }
