@@ -466,16 +466,21 @@ __global__ void __launch_bounds__(kDecWarps * 32, kDecStages == 2 ? 3 : 2) attn_
 // reduction / epilogue of item i, so the fixed per-item latency chain (seq_len -> page table -> TMA -> q reduce -> combine)
 // is paid once per CTA instead of once per wave (B=32: 3.5 waves of one-shot CTAs).
 // ------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persistent_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
+__global__ void __launch_bounds__((kDecWarps + 2) * 32, 2) attn_decode_persistent_kernel(const DecodeAttnCall c, const float* __restrict__ rope_cos,
                                                                                        const float* __restrict__ rope_sin, int n_items) {
+  // warps 0..7: consumers; warp 8: KV page producer (TMA bulk copies); warp 9: q/k/v producer (split-K reduce, deferred norm
+  // scale, RoPE, cache append) -- both producers run ahead of the consumers (KV ring / 2-slot q buffer), so no global-memory
+  // round trip is left on the consumers' per-item critical path.
   constexpr int HD = 128;
   constexpr int NC = kDecWarps * 32;                    // consumer threads
   extern __shared__ __align__(128) uint8_t dsm[];      // [kDecStages][2][PT][HD] bf16
   __shared__ __align__(8) uint64_t s_full[kDecStages];
   __shared__ __align__(8) uint64_t s_empty[kDecStages];
-  __shared__ float s_q[HD];
-  __shared__ float s_k[HD];
-  __shared__ float s_v[HD];
+  __shared__ __align__(8) uint64_t s_qfull[2];
+  __shared__ __align__(8) uint64_t s_qempty[2];
+  __shared__ __align__(16) float s_q[2][HD];
+  __shared__ __align__(16) float s_k[2][HD];
+  __shared__ __align__(16) float s_v[2][HD];
   __shared__ float s_acc[kDecWarps][HD];
   __shared__ float s_m[kDecWarps], s_l[kDecWarps];
 
@@ -485,6 +490,7 @@ __global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persisten
   TraceScope trace(4);
   if (tid == 0) {
     for (int s = 0; s < kDecStages; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), kDecWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&s_qfull[s]), 1); mbar_init(smem_u32(&s_qempty[s]), kDecWarps); }
     fence_barrier_init();
   }
   pdl_launch_dependents();
@@ -493,7 +499,7 @@ __global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persisten
   __syncthreads();
 
   if (warp == kDecWarps) {
-    // ===================== producer warp =====================
+    // ===================== KV page producer =====================
     if (lane == 0) {
       uint32_t n = 0;                                   // pages issued so far (ring position)
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -518,54 +524,76 @@ __global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persisten
     }
     return;
   }
+  if (warp == kDecWarps + 1) {
+    // ===================== q/k/v producer: lane l owns dims [4l, 4l+4) =====================
+    uint32_t qi = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qi) {
+      const int slot = qi & 1;
+      mbar_wait(smem_u32(&s_qempty[slot]), ((qi >> 1) & 1u) ^ 1u);
+      const int b = item / c.H, h = item % c.H;
+      const int L = c.seq_len[b];
+      float q4[4] = {0.f, 0.f, 0.f, 0.f}, k4[4] = {0.f, 0.f, 0.f, 0.f}, v4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int s0 = 0; s0 < c.splits; s0 += 2) {          // two splits (6 x 16 B loads) in flight
+        float4 t[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int sp = s0 + u;
+          const float* row = c.qkv_partial + ((size_t)(sp < c.splits ? sp : 0) * c.ws_rows + b) * (size_t)(3 * T) + h * HD + 4 * lane;
+          const bool ok = sp < c.splits;
+          t[u][0] = ok ? __ldcg(reinterpret_cast<const float4*>(row)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[u][1] = ok ? __ldcg(reinterpret_cast<const float4*>(row + T)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[u][2] = ok ? __ldcg(reinterpret_cast<const float4*>(row + 2 * T)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {                     // fixed split order
+          q4[0] += t[u][0].x; q4[1] += t[u][0].y; q4[2] += t[u][0].z; q4[3] += t[u][0].w;
+          k4[0] += t[u][1].x; k4[1] += t[u][1].y; k4[2] += t[u][1].z; k4[3] += t[u][1].w;
+          v4[0] += t[u][2].x; v4[1] += t[u][2].y; v4[2] += t[u][2].z; v4[3] += t[u][2].w;
+        }
+      }
+      const float rs = c.rstd ? __ldcg(c.rstd + b) : 1.f;
+      const float4 cs4 = *reinterpret_cast<const float4*>(rope_cos + (size_t)L * (HD / 2) + ((4 * lane) & 63));
+      const float4 sn4 = *reinterpret_cast<const float4*>(rope_sin + (size_t)L * (HD / 2) + ((4 * lane) & 63));
+      const float cs[4] = {cs4.x, cs4.y, cs4.z, cs4.w}, sn[4] = {sn4.x, sn4.y, sn4.z, sn4.w};
+      float qo[4], ko[4], vo[4];
+      uint32_t kpk[2], vpk[2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float qv = q4[j] * rs, kv = k4[j] * rs, vv = v4[j] * rs;
+        const float qp = __shfl_xor_sync(0xffffffffu, qv, 16), kp = __shfl_xor_sync(0xffffffffu, kv, 16);   // dims d +- 64
+        const float sgn = (lane < 16) ? -1.f : 1.f;
+        qo[j] = (qv * cs[j] + sgn * qp * sn[j]) * c.scale;
+        ko[j] = __bfloat162float(__float2bfloat16(kv * cs[j] + sgn * kp * sn[j]));     // the cache holds bf16: attend over the rounded values
+        vo[j] = __bfloat162float(__float2bfloat16(vv));
+      }
+      kpk[0] = pack_bf16x2(ko[0], ko[1]); kpk[1] = pack_bf16x2(ko[2], ko[3]);
+      vpk[0] = pack_bf16x2(vo[0], vo[1]); vpk[1] = pack_bf16x2(vo[2], vo[3]);
+      *reinterpret_cast<float4*>(&s_q[slot][4 * lane]) = make_float4(qo[0], qo[1], qo[2], qo[3]);
+      *reinterpret_cast<float4*>(&s_k[slot][4 * lane]) = make_float4(ko[0], ko[1], ko[2], ko[3]);
+      *reinterpret_cast<float4*>(&s_v[slot][4 * lane]) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+      const int page = __ldg(c.page_table + (size_t)b * c.pages_per_seq + L / PT);
+      const int cslot = L % PT;
+      *reinterpret_cast<uint2*>(c.kv_pages + ((((size_t)page * 2 + 0) * c.H + h) * PT + cslot) * HD + 4 * lane) = make_uint2(kpk[0], kpk[1]);
+      *reinterpret_cast<uint2*>(c.kv_pages + ((((size_t)page * 2 + 1) * c.H + h) * PT + cslot) * HD + 4 * lane) = make_uint2(vpk[0], vpk[1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_qfull[slot]));
+    }
+    return;
+  }
 
   // ===================== consumer warps (named barrier 1, NC threads) =====================
   const int grp = lane >> 3, sub = lane & 7;
   const uint32_t gmask = 0xffu << (grp * 8);
-  uint32_t n = 0;
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  uint32_t n = 0, qi = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++qi) {
     const int b = item / c.H, h = item % c.H;
     const int L = c.seq_len[b];
     const int npages = (L + PT - 1) / PT;
-    // ---- q (and the new token's k, v): reduce split-K partials, deferred norm scale, RoPE, append to the cache
-    {
-      const int d = tid & (HD - 1);
-      float qv = 0.f, kv = 0.f, vv = 0.f;
-      if (tid < HD) {
-        for (int s = 0; s < c.splits; ++s) {
-          const float* row = c.qkv_partial + ((size_t)s * c.ws_rows + b) * (size_t)(3 * T);
-          qv += __ldcg(row + h * HD + d);
-          kv += __ldcg(row + T + h * HD + d);
-          vv += __ldcg(row + 2 * T + h * HD + d);
-        }
-        if (c.rstd != nullptr) { const float rs = __ldcg(c.rstd + b); qv *= rs; kv *= rs; vv *= rs; }
-        s_q[d] = qv; s_k[d] = kv; s_v[d] = vv;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
-      float qr = 0.f, kr = 0.f;
-      if (tid < HD) {
-        const float cs = rope_cos[(size_t)L * (HD / 2) + (d & 63)], sn = rope_sin[(size_t)L * (HD / 2) + (d & 63)];
-        const float qp = (d < 64) ? -s_q[d + 64] : s_q[d - 64];
-        const float kp = (d < 64) ? -s_k[d + 64] : s_k[d - 64];
-        qr = (qv * cs + qp * sn) * c.scale;
-        kr = kv * cs + kp * sn;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
-      if (tid < HD) {
-        s_q[d] = qr;
-        const bf16 kb = __float2bfloat16(kr), vb = __float2bfloat16(vv);
-        s_k[d] = __bfloat162float(kb);
-        s_v[d] = __bfloat162float(vb);
-        const int page = c.page_table[(size_t)b * c.pages_per_seq + L / PT];
-        const int slot = L % PT;
-        c.kv_pages[((((size_t)page * 2 + 0) * c.H + h) * PT + slot) * HD + d] = kb;
-        c.kv_pages[((((size_t)page * 2 + 1) * c.H + h) * PT + slot) * HD + d] = vb;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
-    }
+    const int slot = qi & 1;
+    mbar_wait(smem_u32(&s_qfull[slot]), (qi >> 1) & 1u);
     float qreg[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { qreg[i] = s_q[sub * 8 + i]; qreg[8 + i] = s_q[64 + sub * 8 + i]; }
+    for (int i = 0; i < 8; ++i) { qreg[i] = s_q[slot][sub * 8 + i]; qreg[8 + i] = s_q[slot][64 + sub * 8 + i]; }
     float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
@@ -603,10 +631,10 @@ __global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persisten
       if (lane == 0) mbar_arrive(smem_u32(&s_empty[stage]));     // this warp is done with the stage
     }
     __syncwarp();
-    if (warp == 0 && grp == 0) {                                  // the new token, from smem
+    if (warp == 0 && grp == 0) {                                  // the new token, from the q/k/v producer's slot
       float sc = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sc += qreg[i] * s_k[sub * 8 + i] + qreg[8 + i] * s_k[64 + sub * 8 + i];
+      for (int i = 0; i < 8; ++i) sc += qreg[i] * s_k[slot][sub * 8 + i] + qreg[8 + i] * s_k[slot][64 + sub * 8 + i];
       sc += __shfl_xor_sync(0x000000ffu, sc, 1);
       sc += __shfl_xor_sync(0x000000ffu, sc, 2);
       sc += __shfl_xor_sync(0x000000ffu, sc, 4);
@@ -616,11 +644,12 @@ __global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persisten
       l = l * cr + p;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        acc[i] = acc[i] * cr + p * s_v[sub * 8 + i];
-        acc[8 + i] = acc[8 + i] * cr + p * s_v[64 + sub * 8 + i];
+        acc[i] = acc[i] * cr + p * s_v[slot][sub * 8 + i];
+        acc[8 + i] = acc[8 + i] * cr + p * s_v[slot][64 + sub * 8 + i];
       }
     }
     __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&s_qempty[slot]));         // this warp no longer needs the slot
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
       const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
@@ -653,7 +682,7 @@ __global__ void __launch_bounds__((kDecWarps + 1) * 32, 2) attn_decode_persisten
       }
       c.out[(size_t)b * T + h * HD + tid] = __float2bfloat16(O / Lsum);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");          // s_q / s_acc are reused by the next item
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");          // s_acc is reused by the next item
   }
   trace.done();
 }
@@ -695,7 +724,7 @@ int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   if (c.kv_splits == 1 && ((pmode == 1 && n_items > slots) || pmode == 2)) {
     // more (sequence, head) items than resident CTAs: persistent, warp-specialised variant
     cfg.gridDim = dim3(n_items < slots ? n_items : slots);
-    cfg.blockDim = dim3((kDecWarps + 1) * 32);
+    cfg.blockDim = dim3((kDecWarps + 2) * 32);
     VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_persistent_kernel, c, rope_cos_table(), rope_sin_table(), n_items));
     return 0;
   }
