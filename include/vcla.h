@@ -124,6 +124,11 @@ int vcla_prefill(vcla_ctx* ctx, const int64_t* ids_dev, int B, int T, int image_
 int vcla_decode_step(vcla_ctx* ctx, const int32_t* tok_in_dev, int B, float* logits_dev, int32_t* tok_out_dev, int use_graph,
                      vcla_stream stream);
 
+/* n_steps (1..64) greedy decode steps replayed as ONE CUDA graph; tok_inout_dev (int32 (B)) is consumed and rewritten in place by
+ * every step and every chosen token is appended to the history (vcla_read_history).  Same arithmetic as n_steps calls of
+ * vcla_decode_step; amortises the launch gap between steps. */
+int vcla_decode_multi(vcla_ctx* ctx, int32_t* tok_inout_dev, int B, int n_steps, vcla_stream stream);
+
 /* Tokens chosen so far: row 0 = the prefill's argmax, row s = decode step s.  Copies [n_steps, B] int32 to a DEVICE buffer
  * (async on `stream`): lets a greedy loop run as pure graph replays with no per-step host or torch work. */
 int vcla_read_history(vcla_ctx* ctx, int32_t* dst_dev, int B, int n_steps, vcla_stream stream);

@@ -38,6 +38,10 @@ class _StubEngine:
         tok_out.copy_(((tok_in.long() * 31 + self.state + self.pos) % 997).to(torch.int32))
         self.hist.append(tok_out.clone())
 
+    def decode_many(self, tok, n_steps):
+        for _ in range(n_steps):
+            self.decode_step(tok, tok)
+
     def read_history(self, B, n_steps):
         return torch.stack(self.hist[:n_steps], 0)
 

@@ -53,11 +53,12 @@ struct TextLayer {
 };
 
 struct GraphKey {
-  int B; const void* tok_in; const void* logits; const void* tok_out;
+  int B; const void* tok_in; const void* logits; const void* tok_out; int n_steps = 1;
   bool operator<(const GraphKey& o) const {
     if (B != o.B) return B < o.B;
     if (tok_in != o.tok_in) return tok_in < o.tok_in;
     if (logits != o.logits) return logits < o.logits;
+    if (n_steps != o.n_steps) return n_steps < o.n_steps;
     return tok_out < o.tok_out;
   }
 };
@@ -739,19 +740,16 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
   return 0;
 }
 
-int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, int use_graph, vcla_stream stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
-  if (!tok_in || !tok_out) { set_error("decode: null token buffers"); return -1; }
-  if (!use_graph) return decode_enqueue(c, tok_in, B, logits, tok_out, st);
-  GraphKey key{B, tok_in, logits, tok_out};
+static int decode_graph(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, int n_steps, cudaStream_t st) {
+  GraphKey key{B, tok_in, logits, tok_out, n_steps};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
     const int64_t before = c->launches;
     cudaGraph_t graph = nullptr;
     if (!c->cap_stream) VCLA_CUDA_OK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
     VCLA_CUDA_OK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int rc = decode_enqueue(c, tok_in, B, logits, tok_out, c->cap_stream);
+    int rc = 0;
+    for (int i = 0; i < n_steps && rc == 0; ++i) rc = decode_enqueue(c, tok_in, B, logits, tok_out, c->cap_stream);
     cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (rc != 0) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return -1; }
     if (e != cudaSuccess) { set_error("decode: graph capture failed: %s", cudaGetErrorString(e)); return -1; }
@@ -767,6 +765,22 @@ int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, i
   VCLA_CUDA_OK(cudaGraphLaunch(it->second, st));
   c->launches += c->graph_launches[key];
   return 0;
+}
+
+int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, int use_graph, vcla_stream stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
+  if (!tok_in || !tok_out) { set_error("decode: null token buffers"); return -1; }
+  if (!use_graph) return decode_enqueue(c, tok_in, B, logits, tok_out, st);
+  return decode_graph(c, tok_in, B, logits, tok_out, 1, st);
+}
+
+int vcla_decode_multi(vcla_ctx* c, int32_t* tok_inout, int B, int n_steps, vcla_stream stream) {
+  // n_steps greedy decode steps captured back to back in ONE CUDA graph (the token buffer is consumed and rewritten in place,
+  // every chosen token is appended to the device-side history): amortises the gap between consecutive graph launches.
+  if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
+  if (!tok_inout || n_steps < 1 || n_steps > 64) { set_error("decode_multi: bad arguments"); return -1; }
+  return decode_graph(c, tok_inout, B, nullptr, tok_inout, n_steps, (cudaStream_t)stream);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -46,6 +46,7 @@ _SIGNATURES = [
     ("vcla_vision_encode", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     ("vcla_prefill", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     ("vcla_decode_step", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
+    ("vcla_decode_multi", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     ("vcla_read_history", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     ("vcla_kernel_launches", C.c_int64, [_P, C.c_int]),
     ("vcla_read_stage", C.c_int, [_P, C.c_char_p, C.c_int, _P, _P]),

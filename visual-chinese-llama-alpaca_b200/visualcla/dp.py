@@ -69,8 +69,7 @@ def generate_dp(model, input_ids: torch.Tensor, pixel_values: Optional[torch.Ten
         phase_hook("prefill_done")
     if world == 1 and step_hook is None:
         # single GPU: the graph appends every chosen token to a device-side history -> the loop is pure graph replays
-        for step in range(1, max_new_tokens):
-            eng.decode_step(tok[:nloc], tok[:nloc], None)
+        eng.decode_many(tok[:nloc], max_new_tokens - 1)
         out.copy_(eng.read_history(nloc, max_new_tokens).t())
     else:
         for step in range(max_new_tokens):

@@ -150,6 +150,18 @@ class Engine:
             N.check(self.lib.vcla_decode_step(self._ctx, N.ptr(tok_in), B, N.ptr(logits), N.ptr(tok_out), 1 if use_graph else 0,
                                               self._stream()), "vcla_decode_step")
 
+    GRAPH_CHUNK = 16     # decode steps per CUDA graph in the fixed-length greedy loop
+
+    def decode_many(self, tok: torch.Tensor, n_steps: int):
+        """n_steps greedy steps on the in-place int32 token buffer `tok` (B,), replayed in graphs of GRAPH_CHUNK steps."""
+        B = tok.shape[0]
+        left = n_steps
+        with torch.cuda.device(self.device):
+            while left > 0:
+                k = self.GRAPH_CHUNK if left >= self.GRAPH_CHUNK else 1
+                N.check(self.lib.vcla_decode_multi(self._ctx, N.ptr(tok), B, k, self._stream()), "vcla_decode_multi")
+                left -= k
+
     def read_history(self, B: int, n_steps: int) -> torch.Tensor:
         """(n_steps, B) int32 CUDA tensor: tokens chosen by the prefill (row 0) and each decode step since."""
         out = torch.empty(n_steps, B, dtype=torch.int32, device=self.device)

@@ -434,8 +434,7 @@ class VisualCLAModel:
         if not need_logits and not eos and not crit:
             # pure greedy, fixed length: graph replays only; tokens come from the device-side history the graph appends to
             tok.copy_(first_tok)
-            for _ in range(1, max_new):
-                eng.decode_step(tok, tok, None)
+            eng.decode_many(tok, max_new - 1)
             result = eng.read_history(B, max_new).t().to(torch.int64)
             if getattr(gc, "return_dict_in_generate", False):
                 return SimpleNamespace(sequences=result, logits=None, scores=None)
