@@ -158,7 +158,9 @@ class Engine:
         left = n_steps
         with torch.cuda.device(self.device):
             while left > 0:
-                k = self.GRAPH_CHUNK if left >= self.GRAPH_CHUNK else 1
+                k = self.GRAPH_CHUNK
+                while k > left:
+                    k >>= 1                       # power-of-two tails: at most log2(GRAPH_CHUNK)+1 graph variants
                 N.check(self.lib.vcla_decode_multi(self._ctx, N.ptr(tok), B, k, self._stream()), "vcla_decode_multi")
                 left -= k
 
