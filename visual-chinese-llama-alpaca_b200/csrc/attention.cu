@@ -27,7 +27,8 @@ template <int HD>
 __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   constexpr int BQ = 64, BKV = 64, CHUNKS = HD / 8;
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem), sK = sQ + BQ * HD * 2, sV = sK + BKV * HD * 2;
+  const uint32_t sQ = smem_u32(smem), sKV0 = sQ + BQ * HD * 2;   // then 2 x {K tile, V tile} (double buffered)
+  constexpr uint32_t kTileBytes = BKV * HD * 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int Sk = c.n0 + c.n1;
@@ -59,8 +60,8 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   if (c.causal) kv_end = min(Sk, q0 + BQ + off);
   const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;  // the two query rows this thread owns
 
-  for (int j0 = (kv0 / BKV) * BKV; j0 < kv_end; j0 += BKV) {
-    __syncthreads();  // previous tile fully consumed
+  auto load_kv_tile = [&](int j0, int buf) {
+    const uint32_t sKb = sKV0 + (uint32_t)buf * 2u * kTileBytes, sVb = sKb + kTileBytes;
     for (int i = tid; i < BKV * CHUNKS; i += 128) {
       int r = i / CHUNKS, ch = i % CHUNKS;
       int j = j0 + r;
@@ -74,12 +75,21 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
         size_t ro = (size_t)(b * c.n1 + (j - c.n0)) * c.kv1_stride + h * HD + ch * 8;
         ks = c.k1 + ro; vs = c.v1 + ro;
       }
-      cp_async_16(sK + swz<HD>(r, ch), ks, ok);
-      cp_async_16(sV + swz<HD>(r, ch), vs, ok);
+      cp_async_16(sKb + swz<HD>(r, ch), ks, ok);
+      cp_async_16(sVb + swz<HD>(r, ch), vs, ok);
     }
     cp_async_commit();
-    cp_async_wait<0>();
+  };
+  const int j_first = (kv0 / BKV) * BKV;
+  if (j_first < kv_end) load_kv_tile(j_first, 0);
+  int buf = 0;
+  for (int j0 = j_first; j0 < kv_end; j0 += BKV, buf ^= 1) {
+    // prefetch the next K/V tile into the other buffer while this one is consumed
+    const bool has_next = (j0 + BKV) < kv_end;
+    if (has_next) load_kv_tile(j0 + BKV, buf ^ 1);
+    if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
+    const uint32_t sK = sKV0 + (uint32_t)buf * 2u * kTileBytes, sV = sK + kTileBytes;
 
     // ---- S = Q K^T  (16 x 64 per warp)
     float s[BKV / 8][4];
@@ -159,6 +169,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
         mma_bf16_16816(o_acc[nd + 1], a, b1);
       }
     }
+    __syncthreads();   // all warps are done with this buffer before the next iteration's prefetch overwrites it
   }
   // ---- finalise: O / l  (l summed over the 4 lanes that share a row)
 #pragma unroll
@@ -189,21 +200,22 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
     return -1;
   }
   dim3 grid((c.Sq + 63) / 64, c.H, c.B);
-  const size_t smem = 3 * 64 * c.HD * 2;
+  const size_t smem = 5 * 64 * c.HD * 2;     // Q + 2 x (K, V) tiles
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   int na = 0;
   if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   cfg.attrs = attr; cfg.numAttrs = na;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VCLA_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 128 * 2));
+    VCLA_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 64 * 2));
+    attr_set = true;
+  }
   if (c.HD == 64) {
     VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_prefill_kernel<64>, c));
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      VCLA_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
     VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_prefill_kernel<128>, c));
   }
   return 0;
