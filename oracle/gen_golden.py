@@ -6,7 +6,7 @@ on seeded synthetic weights.  Run in the authoring container only:
 The fixtures pin oracle/visualcla_oracle.py (tests/test_oracle_golden.py) and, through it and
 directly, the CUDA path (tests/test_parity_gpu.py).  Weights are NOT stored: they are
 regenerated bit-exactly from (config, seed) by the integer-hash generator
-(oracle: hash_normal_bf16; device: csrc/weights.cu).
+(oracle: hash_normal_bf16; device: csrc/elementwise.cu fill_hash_normal_kernel).
 """
 import os
 import sys

@@ -122,8 +122,8 @@ def tiny_config() -> PathConfig:
 
 # --------------------------------------------------------------------------------------
 # deterministic synthetic weights (integer hash -> Irwin-Hall(4) pseudo-normal)
-# bit-identical to the device generator in csrc/weights.cu (pure integer arithmetic +
-# one fp32 multiply + RNE round to bf16).
+# bit-identical to the device generator `fill_hash_normal_kernel` in csrc/elementwise.cu (pure integer
+# arithmetic + one fp32 multiply + one fp32 add + RNE round to bf16).
 # --------------------------------------------------------------------------------------
 _IH_SIGMA = 65536.0 / math.sqrt(3.0)      # std of the sum of four uniform u16
 
