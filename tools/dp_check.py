@@ -5,22 +5,24 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "visual-chinese-llama-alpaca_b200"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import visualcla  # noqa: E402
-import visualcla_oracle as O  # noqa: E402
 from visualcla.dp import generate_dp  # noqa: E402
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-cfg = O.PathConfig(v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=2, t_vocab=2003)
+from visualcla.engine import path_config_7b  # noqa: E402
+cfg = dict(path_config_7b(), v_layers=1, r_layers=1, t_hidden=512, t_heads=4, t_ffn=1408, t_layers=2, t_vocab=2003)
 B, n_new = 6, 12
-m = visualcla.VisualCLAModel.from_synthetic(cfg.to_dict(), seed=9, max_batch=B, max_seq=160)
+m = visualcla.VisualCLAModel.from_synthetic(cfg, seed=9, max_batch=B, max_seq=160)
 m.image_at_head = True
-px, ids = O.make_inputs(cfg, B, 20, seed=5)
+g = torch.Generator().manual_seed(5)
+px = torch.randn(B, 3, cfg["v_image"], cfg["v_image"], generator=g)
+ids = torch.randint(3, cfg["t_vocab"] - 4, (B, 20), generator=g)
+ids[:, 0], ids[:, 1], ids[:, 2] = 1, cfg["t_vocab"] - 4, cfg["t_vocab"] - 3
 dp = generate_dp(m, ids, px, n_new)                     # every rank: its slice + per-step NCCL all-gather
 single = m.generate(input_ids=ids.cuda(), pixel_values=px.cuda(), do_sample=False, max_new_tokens=n_new, eos_token_id=None, pad_token_id=0)
 ok = torch.equal(dp, single)
