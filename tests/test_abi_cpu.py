@@ -35,6 +35,64 @@ def test_binding_covers_header():
     assert sorted(_native.EXPORTED_SYMBOLS) == _header_symbols()
 
 
+def _header_text():
+    txt = open(os.path.join(ROOT, "include", "vcla.h")).read()
+    return re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+
+
+def _c_kind(decl):
+    decl = decl.strip()
+    if "*" in decl or "[" in decl or decl.startswith("vcla_stream"):      # arrays decay to pointers
+        return "ptr"
+    for prefix, kind in (("float", "float"), ("int64_t", "i64"), ("uint32_t", "u32"), ("int", "int")):
+        if decl.startswith(prefix):
+            return kind
+    raise AssertionError(f"unclassified C parameter: {decl!r}")
+
+
+def _py_kind(t):
+    if t is C.c_float:
+        return "float"
+    if t is C.c_int64:
+        return "i64"
+    if t is C.c_uint32:
+        return "u32"
+    if t is C.c_int:
+        return "int"
+    return "ptr"            # c_void_p / c_char_p / POINTER(...)
+
+
+def test_binding_argtypes_match_prototypes():
+    """Every ctypes signature has the arity and the per-argument class (pointer / int / int64 / float) of the C prototype:
+    a 64-bit pointer passed as a default-int, or a float passed as an int, would corrupt the call silently."""
+    from visualcla import _native
+    protos = {}
+    for m in re.finditer(r"[\w\s\*]+?\b(vcla_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", _header_text()):
+        args = m.group(2).replace("\n", " ").strip()
+        protos[m.group(1)] = [] if args in ("", "void") else [a for a in args.split(",")]
+    assert sorted(protos) == _header_symbols()
+    for name, _res, argtypes in _native._SIGNATURES:
+        want = [_c_kind(a) for a in protos[name]]
+        got = [_py_kind(t) for t in argtypes]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
+
+
+def test_config_struct_matches_header():
+    """VclaConfig's field order and types are those of `vcla_config` in include/vcla.h."""
+    from visualcla import _native
+    body = re.search(r"typedef struct \{(.*?)\} vcla_config;", _header_text(), flags=re.S).group(1)
+    fields = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        ctype, names = stmt.split(None, 1)
+        fields += [(n.strip(), ctype) for n in names.split(",")]
+    want = [(n, {"int": C.c_int, "float": C.c_float}[t]) for n, t in fields]
+    assert list(_native.VclaConfig._fields_) == want
+    assert C.sizeof(_native.VclaConfig) == 4 * len(want)
+
+
 def test_version_and_error_strings(lib):
     assert b"sm_100a" in lib.vcla_version()
     assert isinstance(lib.vcla_last_error(), bytes)
@@ -71,3 +129,7 @@ def test_product_never_imports_oracle():
             elif f.endswith((".cu", ".cuh", ".h")):
                 for line in open(path):
                     assert not ("#include" in line and "oracle" in line), (path, line)
+    for f in os.listdir(os.path.join(ROOT, "tools")):           # the developer tools drive the product path only
+        if f.endswith(".py"):
+            for line in open(os.path.join(ROOT, "tools", f)):
+                assert not re.match(r"\s*(import|from)\s+\S*oracle", line), (f, line)
