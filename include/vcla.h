@@ -165,6 +165,27 @@ int vcla_trace_read(vcla_ctx* ctx, uint64_t* dst_host, int max_events, int* n_ev
 /* enable/disable programmatic dependent launch for subsequently enqueued kernels (process-wide) */
 void vcla_set_pdl(int on);
 
+/* ---- image pre-processing (the step before the path) ------------------------ */
+/* Replaces HF CLIPImageProcessor's PIL pipeline as the reference calls it for every request
+ * (models/visualcla/modeling_utils.py:130 builds it, :150-152 / :187-189 call it):
+ *   resize(shortest_edge = out_size, BICUBIC) -> center_crop(out_size) -> x * 1/255 -> (x - mean) / std
+ * The resize is Pillow's 8-bit ImagingResample (antialiased separable bicubic, 22-bit taps, clip after each pass,
+ * horizontal first) and the result is bit-identical to it.  No context needed: the caller owns every buffer.
+ *
+ * vcla_preprocess_workspace_bytes: device scratch one call needs for a (height, width) picture; -1 if unsupported
+ *   (sides 1..32768, out_size 1..4096, resized long side <= 65536).  Host-only, no GPU needed.
+ * vcla_resample_taps: Pillow's tap table of one axis (host-only): first[out], count[out], taps[out][ksize] with 22
+ *   fractional bits.  Returns ksize; with all three pointers NULL only returns ksize.  -1 on error.
+ * vcla_preprocess_image: rgb_dev = (height, width, 3) uint8 RGB in device memory; pixel_values_dev = (3, out_size,
+ *   out_size) in `dtype` (VCLA_F32 / F16 / BF16, round-to-nearest from the float32 result); mean3/std3 = host floats.
+ *   Builds the tap tables on the host, uploads them into the workspace and enqueues two kernels on `stream`.  The
+ *   workspace must be 16-byte aligned and stay untouched until the stream has run them. */
+int64_t vcla_preprocess_workspace_bytes(int height, int width, int out_size);
+int vcla_resample_taps(int in_size, int out_size, int32_t* first, int32_t* count, int32_t* taps, int ksize_capacity);
+int vcla_preprocess_image(const uint8_t* rgb_dev, int height, int width, int out_size, const float* mean3,
+                          const float* std3, void* workspace_dev, int64_t workspace_bytes, void* pixel_values_dev,
+                          int dtype, vcla_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

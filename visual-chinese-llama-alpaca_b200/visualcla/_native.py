@@ -59,6 +59,10 @@ _SIGNATURES = [
     ("vcla_trace_enable", C.c_int, [_P, C.c_int]),
     ("vcla_trace_read", C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int)]),
     ("vcla_set_pdl", None, [C.c_int]),
+    ("vcla_preprocess_workspace_bytes", C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    ("vcla_resample_taps", C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int]),
+    ("vcla_preprocess_image", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int64, _P,
+                                        C.c_int, _P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
