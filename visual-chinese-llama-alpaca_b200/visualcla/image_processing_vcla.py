@@ -7,7 +7,8 @@ all in PIL/numpy.  This class has the same call surface (`proc(image, return_ten
 csrc/preprocess.cu (`vcla_preprocess_image`): Pillow's 8-bit bicubic resample reproduced bit for bit, only the cropped
 window computed, result left in HBM in the dtype the vision tower wants.
 
-Opt-in: `get_model_and_tokenizer_and_processor` still returns the HF processor; swap it with
+Opt-in: `get_model_and_tokenizer_and_processor` returns the HF processor unless the environment
+sets VCLA_GPU_PREPROCESS=1; or swap it by hand with
     model.image_processor = VclaImageProcessor.from_pretrained(vision_dir, patch_size=model.image_processor.patch_size)
 There is no CPU fallback: without libvcla.so or a CUDA device the call raises.
 """

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import gc
 import logging
+import os
 import queue
 import threading
 from copy import deepcopy
@@ -96,7 +97,12 @@ def get_model_and_tokenizer_and_processor(visualcla_model=None, text_model=None,
         model = VisualCLAModel.from_vision_text_pretrained(vision_model, text_model, visualcla_config=VisualCLAConfig.from_pretrained(lora_model),
                                                            torch_dtype=torch_dtype, default_device=default_device,
                                                            device_map=device_map, load_in_8bit=load_in_8bit, **engine_kwargs)
-    image_processor = CLIPImageProcessor.from_pretrained(vision_model or visualcla_model)
+    if os.environ.get("VCLA_GPU_PREPROCESS", "") not in ("", "0"):
+        # opt-in: same pre-processing (Pillow-exact) on the device, pixel_values never leave HBM (image_processing_vcla.py)
+        from .image_processing_vcla import VclaImageProcessor
+        image_processor = VclaImageProcessor.from_pretrained(vision_model or visualcla_model)
+    else:
+        image_processor = CLIPImageProcessor.from_pretrained(vision_model or visualcla_model)
     image_processor.patch_size = model.vision_model.config.patch_size
     model.tokenizer = tokenizer
     model.image_processor = image_processor
