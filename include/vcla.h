@@ -78,9 +78,12 @@ int vcla_weight_count(const vcla_ctx* ctx);
 /* kind: 0 = matrix stored bf16, 1 = vector/table stored f32.  shape has up to 4 dims. */
 int vcla_weight_info(const vcla_ctx* ctx, int index, const char** name, int64_t shape[4], int* ndim, int* kind);
 /* Copy + repack one tensor into the arena (fused QKV, gate/up interleave, K padding).  `src` is a host
- * pointer (on_device = 0) or device pointer (on_device = 1) to the contiguous tensor in `dtype`.
+ * pointer (on_device = 0) or device pointer (on_device = 1) to the contiguous tensor in `dtype` holding `numel`
+ * elements; the call fails (nothing is read) unless numel equals the element count of the named tensor, so a
+ * checkpoint whose shape disagrees with the config is an error, never an out-of-bounds read.
  * Replaces from_merged_pretrained's loading (modeling_visualcla.py:120-181).  Synchronises the stream. */
-int vcla_load_weight(vcla_ctx* ctx, const char* name, const void* src, int dtype, int on_device, vcla_stream stream);
+int vcla_load_weight(vcla_ctx* ctx, const char* name, const void* src, int dtype, int64_t numel, int on_device,
+                     vcla_stream stream);
 /* Copy one logical tensor back to host: bf16 for kind 0, f32 for kind 1 (state_dict() equivalent). */
 int vcla_read_weight(vcla_ctx* ctx, const char* name, void* dst_host, vcla_stream stream);
 /* Deterministic synthetic weights: w = mean + std * IrwinHall4(hash(name, seed, index)), bit-identical
@@ -88,8 +91,20 @@ int vcla_read_weight(vcla_ctx* ctx, const char* name, void* dst_host, vcla_strea
 int vcla_init_synthetic(vcla_ctx* ctx, uint32_t seed, vcla_stream stream);
 
 /* ---- the hot path ----------------------------------------------------------------------------- */
-/* Drop all sequences (KV cache lengths -> 0). */
+/* Drop all sequences (KV cache lengths -> 0, every KV page back on the free stack). */
 int vcla_reset(vcla_ctx* ctx, vcla_stream stream);
+
+/* Paged KV cache (the reference's DynamicCache, HF:cache_utils.py:88-120, re-designed): physical pages of `page_tokens`
+ * tokens are handed to sequences on demand by a device-side allocator that runs inside the stream / the decode CUDA graph
+ * (pages are assigned round-robin as sequences grow, so one sequence's pages are NOT contiguous; every kernel goes through
+ * the page table).  vcla_decode_* fail with an error instead of running past max_seq.
+ *   vcla_kv_geometry     pages per sequence (table row length), pages in the pool, tokens per page
+ *   vcla_kv_read_pages   synchronous copy to the host of the page table (max_batch x pages_per_seq int32), the pages owned
+ *                        per sequence (max_batch int32) and {free pages, exhausted flag} (2 int32); any pointer may be NULL
+ *   vcla_kv_debug_shuffle  test hook: permute the order in which free pages are handed out (then resets the context) */
+int vcla_kv_geometry(const vcla_ctx* ctx, int* pages_per_seq, int* total_pages, int* page_tokens);
+int vcla_kv_read_pages(vcla_ctx* ctx, int32_t* table_host, int32_t* npages_host, int32_t* state_host);
+int vcla_kv_debug_shuffle(vcla_ctx* ctx, uint32_t seed);
 
 /* pixels (B,3,I,I) NCHW -> image embeddings (B, r_queries, t_hidden), kept inside the context for the
  * next vcla_prefill and optionally copied to `out_dev_f32`.  Replaces
@@ -132,6 +147,27 @@ int vcla_decode_multi(vcla_ctx* ctx, int32_t* tok_inout_dev, int B, int n_steps,
 /* Tokens chosen so far: row 0 = the prefill's argmax, row s = decode step s.  Copies [n_steps, B] int32 to a DEVICE buffer
  * (async on `stream`): lets a greedy loop run as pure graph replays with no per-step host or torch work. */
 int vcla_read_history(vcla_ctx* ctx, int32_t* dst_dev, int B, int n_steps, vcla_stream stream);
+
+/* ---- data parallel over the GPUs of one box (the reference has no DP of its own) ----------------
+ * Requests are independent through the whole path, so each rank (one process + one context per GPU) runs a contiguous slice of
+ * the batch and the ONLY exchange is one NCCL all-gather of the chosen token ids per decode step.  After vcla_nccl_init the
+ * exchange is part of the path itself: vcla_prefill and every decode step (also inside the CUDA graphs of vcla_decode_multi)
+ * all-gather `width` int32 slots per rank on a forked stream branch -- off the step's critical path, joined before the send
+ * buffer is rewritten -- and append them to a device-side global history.
+ *   vcla_nccl_unique_id   rank 0 creates the 128-byte ncclUniqueId and ships it to the other ranks by any means
+ *   vcla_nccl_init        width = slots per rank (the largest shard's batch, <= 64); collective over all ranks
+ *   vcla_allgather_tokens plain all-gather of n int32 per rank on `stream` (the non-graph building block)
+ *   vcla_dp_set_active    the exchange is part of vcla_prefill / vcla_decode_* only while active (off after init): every rank must
+ *                         then make the same sequence of calls; a rank-local generation runs with it off
+ *   vcla_dp_exchange      one step's exchange without compute (a rank that holds no requests: global batch < world size)
+ *   vcla_read_history_dp  [n_steps][world * width] int32 -> device buffer: row 0 = prefill argmax of every rank, row s = step s
+ * NCCL is bound with dlopen("libnccl.so.2") at the first of these calls; single-GPU use never loads it. */
+int vcla_nccl_unique_id(uint8_t* out128);
+int vcla_nccl_init(vcla_ctx* ctx, const uint8_t* id128, int rank, int world, int width);
+int vcla_allgather_tokens(vcla_ctx* ctx, const int32_t* local_dev, int n, int32_t* all_dev, vcla_stream stream);
+int vcla_dp_set_active(vcla_ctx* ctx, int on);
+int vcla_dp_exchange(vcla_ctx* ctx, vcla_stream stream);
+int vcla_read_history_dp(vcla_ctx* ctx, int32_t* dst_dev, int n_steps, vcla_stream stream);
 
 /* number of this library's kernels launched by the context since the last call with reset != 0 */
 int64_t vcla_kernel_launches(vcla_ctx* ctx, int reset);

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <mutex>
 #include <stdlib.h>
 
 namespace vcla {
@@ -207,12 +208,7 @@ int attention_prefill(const AttnCall& c, cudaStream_t st) {
   int na = 0;
   if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   cfg.attrs = attr; cfg.numAttrs = na;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VCLA_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 128 * 2));
-    VCLA_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * 64 * 2));
-    attr_set = true;
-  }
+  if (attention_init()) return -1;
   if (c.HD == 64) {
     VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_prefill_kernel<64>, c));
   } else {
@@ -701,24 +697,26 @@ __global__ void __launch_bounds__((kDecWarps + 2) * 32, 2) attn_decode_persisten
 
 VCLA_DEFINE_TRACE_SETTER(trace_set_attention)
 
-// rope table owned by elementwise.cu
-const float* rope_cos_table();
-const float* rope_sin_table();
-
-int attention_decode_init() {
-  static bool done = false;
-  if (done) return 0;
-  VCLA_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecStages * kDecMaxPT * 128 * 2 * 2));
-  VCLA_CUDA_OK(cudaFuncSetAttribute(attn_decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecStages * kDecMaxPT * 128 * 2 * 2));
-  done = true;
-  return 0;
+int attention_init() {
+  // dynamic shared-memory opt-ins of every attention kernel; called once per process from vcla_create (never during capture)
+  static std::once_flag once;
+  static int rc = 0;
+  std::call_once(once, [] {
+    auto set = [](const void* fn, int bytes) { return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : -1; };
+    rc |= set((const void*)attn_decode_kernel, kDecStages * kDecMaxPT * 128 * 2 * 2);
+    rc |= set((const void*)attn_decode_persistent_kernel, kDecStages * kDecMaxPT * 128 * 2 * 2);
+    rc |= set((const void*)attn_prefill_kernel<128>, 5 * 64 * 128 * 2);
+    rc |= set((const void*)attn_prefill_kernel<64>, 5 * 64 * 64 * 2);
+    if (rc) set_error("attention_init: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+  });
+  return rc;
 }
 
 int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   if (c.HD != 128) { set_error("attention_decode: head dim %d unsupported (128)", c.HD); return -1; }
   if (c.page_tokens > kDecMaxPT || c.page_tokens % 8 != 0) { set_error("attention_decode: page_tokens %d unsupported (<= %d, multiple of 8)", c.page_tokens, kDecMaxPT); return -1; }
-  if (rope_cos_table() == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
-  if (attention_decode_init()) return -1;
+  if (c.rope_cos == nullptr || c.rope_sin == nullptr) { set_error("attention_decode: rope table not initialised"); return -1; }
+  if (attention_init()) return -1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(c.kv_splits, c.H, c.B); cfg.blockDim = dim3(kDecWarps * 32);
   cfg.dynamicSmemBytes = (size_t)kDecStages * c.page_tokens * 128 * 2 * 2; cfg.stream = st;
@@ -728,19 +726,18 @@ int attention_decode(const DecodeAttnCall& c, cudaStream_t st) {
   cfg.attrs = attr; cfg.numAttrs = na;
   const int n_items = c.B * c.H;
   int slots = 2 * num_sms();
-  // VCLA_ATTN_PERSISTENT: 0 = never, 1 (default) = when items outnumber the resident CTAs, 2 = whenever kv_splits == 1 (tests);
-  // VCLA_ATTN_PERSISTENT_GRID caps the persistent grid (tests: several items per CTA on small problems)
-  const char* pe = getenv("VCLA_ATTN_PERSISTENT");
-  const int pmode = pe ? atoi(pe) : 1;
-  if (const char* ge = getenv("VCLA_ATTN_PERSISTENT_GRID")) { const int g2 = atoi(ge); if (g2 > 0 && g2 < slots) slots = g2; }
-  if (c.kv_splits == 1 && ((pmode == 1 && n_items > slots) || pmode == 2)) {
+  // persistent_mode: 0 = never, 1 (default) = when items outnumber the resident CTAs, 2 = whenever kv_splits == 1 (tests);
+  // persistent_grid caps the persistent grid (tests: several items per CTA on small problems).  Both are read from the
+  // environment once per context (vcla_create), not per launch.
+  if (c.persistent_grid > 0 && c.persistent_grid < slots) slots = c.persistent_grid;
+  if (c.kv_splits == 1 && ((c.persistent_mode == 1 && n_items > slots) || c.persistent_mode == 2)) {
     // more (sequence, head) items than resident CTAs: persistent, warp-specialised variant
     cfg.gridDim = dim3(n_items < slots ? n_items : slots);
     cfg.blockDim = dim3((kDecWarps + 2) * 32);
-    VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_persistent_kernel, c, rope_cos_table(), rope_sin_table(), n_items));
+    VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_persistent_kernel, c, c.rope_cos, c.rope_sin, n_items));
     return 0;
   }
-  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_kernel, c, rope_cos_table(), rope_sin_table()));
+  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_decode_kernel, c, c.rope_cos, c.rope_sin));
   return 0;
 }
 

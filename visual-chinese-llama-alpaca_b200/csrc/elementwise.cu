@@ -285,16 +285,8 @@ int gather_last_rows(const float* hidden, int B, int S, int D, float* dst, cudaS
 // ------------------------------------------------------------------------------------------------
 // RoPE tables (fp32, computed once on the host the way HF does: HF:models/llama/modeling_llama.py:98-141)
 // ------------------------------------------------------------------------------------------------
-static float* g_rope_cos = nullptr;
-static float* g_rope_sin = nullptr;
-static int g_rope_pos = 0, g_rope_half = 0;
-static float g_rope_theta = 0.f;
-const float* rope_cos_table() { return g_rope_cos; }
-const float* rope_sin_table() { return g_rope_sin; }
-int rope_init(int max_pos, int head_dim, float theta) {
+int rope_fill_tables(int max_pos, int head_dim, float theta, float* cos_dev, float* sin_dev) {
   const int half = head_dim / 2;
-  if (g_rope_cos && g_rope_pos >= max_pos && g_rope_half == half && g_rope_theta == theta) return 0;
-  if (g_rope_cos) { cudaFree(g_rope_cos); cudaFree(g_rope_sin); g_rope_cos = g_rope_sin = nullptr; }
   std::vector<float> hc((size_t)max_pos * half), hs((size_t)max_pos * half);
   for (int i = 0; i < half; ++i) {
     const float inv = 1.0f / powf(theta, (float)(2 * i) / (float)head_dim);
@@ -304,11 +296,8 @@ int rope_init(int max_pos, int head_dim, float theta) {
       hs[(size_t)p * half + i] = (float)sin((double)f);
     }
   }
-  VCLA_CUDA_OK(cudaMalloc(&g_rope_cos, hc.size() * 4));
-  VCLA_CUDA_OK(cudaMalloc(&g_rope_sin, hs.size() * 4));
-  VCLA_CUDA_OK(cudaMemcpy(g_rope_cos, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
-  VCLA_CUDA_OK(cudaMemcpy(g_rope_sin, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
-  g_rope_pos = max_pos; g_rope_half = half; g_rope_theta = theta;
+  VCLA_CUDA_OK(cudaMemcpy(cos_dev, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+  VCLA_CUDA_OK(cudaMemcpy(sin_dev, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -364,11 +353,10 @@ __global__ void rope_and_cache_kernel(bf16* __restrict__ qkv, int S, int H, int 
     *reinterpret_cast<uint4*>(vd + i + half) = *reinterpret_cast<const uint4*>(v + i + half);
   }
 }
-int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table, int pages_per_seq,
-                   int page_tokens, const int32_t* left_pad, int pos_from_mask, cudaStream_t st) {
-  (void)theta;
-  if (!g_rope_cos) { set_error("rope table not initialised"); return -1; }
-  VCLA_LAUNCH(rope_and_cache_kernel, dim3(S, B), dim3(256), 0, st, qkv, S, H, HD, (const float*)g_rope_cos, (const float*)g_rope_sin,
+int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, const float* rope_cos, const float* rope_sin, bf16* kv_pages,
+                   const int32_t* page_table, int pages_per_seq, int page_tokens, const int32_t* left_pad, int pos_from_mask, cudaStream_t st) {
+  if (!rope_cos || !rope_sin) { set_error("rope table not initialised"); return -1; }
+  VCLA_LAUNCH(rope_and_cache_kernel, dim3(S, B), dim3(256), 0, st, qkv, S, H, HD, rope_cos, rope_sin,
               kv_pages, page_table, pages_per_seq, page_tokens, left_pad, pos_from_mask);
   return 0;
 }
@@ -459,7 +447,7 @@ int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf
 }
 
 // logits + argmax: stage 1 per (vocab chunk, b) -> candidate ; stage 2 per b
-constexpr int kArgChunks = 32;
+constexpr int kArgChunks = kArgmaxChunks;
 __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits, int ws_rows, int ldp, int V, float* __restrict__ logits,
                                   int ld_logits, float* __restrict__ cand_val, int* __restrict__ cand_idx, const float* __restrict__ rstd) {
   __shared__ float sv[32];
@@ -503,7 +491,7 @@ __global__ void dec_logits_stage1(const float* __restrict__ partial, int splits,
   }
 }
 __global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int32_t* __restrict__ tok,
-                                  int32_t* __restrict__ history, const int32_t* __restrict__ step_idx) {
+                                  int32_t* __restrict__ history, const int32_t* __restrict__ step_idx, int32_t* __restrict__ dp_send) {
   TraceScope trace(11);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
@@ -519,49 +507,118 @@ __global__ void dec_logits_stage2(const float* __restrict__ cand_val, const int*
   if (lane == 0) {
     tok[b] = bi;
     if (history) history[(size_t)(*step_idx) * gridDim.x + b] = bi;   // [step][B] log of every chosen token since the prefill
+    if (dp_send) dp_send[b] = bi;                                      // send buffer of the per-step token all-gather (data parallel)
   }
 }
-static float* g_cand_val = nullptr;
-static int* g_cand_idx = nullptr;
-static int g_cand_cap = 0;
-int argmax_scratch_init(int max_batch) {
-  if (g_cand_cap >= max_batch) return 0;
-  if (g_cand_val) { cudaFree(g_cand_val); cudaFree(g_cand_idx); }
-  VCLA_CUDA_OK(cudaMalloc(&g_cand_val, (size_t)max_batch * kArgChunks * 4));
-  VCLA_CUDA_OK(cudaMalloc(&g_cand_idx, (size_t)max_batch * kArgChunks * 4));
-  g_cand_cap = max_batch;
-  return 0;
-}
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, int32_t* tok,
-                      int32_t* history, const int32_t* step_idx, const float* rstd, cudaStream_t st) {
-  if (g_cand_cap < B) { set_error("argmax scratch too small (%d < %d)", g_cand_cap, B); return -1; }
-  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, g_cand_val, g_cand_idx, rstd);
-  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)g_cand_val, (const int*)g_cand_idx, tok, history, step_idx);
+                      int32_t* history, const int32_t* step_idx, const float* rstd, float* cand_val, int32_t* cand_idx, int32_t* dp_send, cudaStream_t st) {
+  if (!cand_val || !cand_idx) { set_error("argmax scratch missing"); return -1; }
+  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, cand_val, (int*)cand_idx, rstd);
+  VCLA_LAUNCH(dec_logits_stage2, dim3(B), dim3(32), 0, st, (const float*)cand_val, (const int*)cand_idx, tok, history, step_idx, dp_send);
   return 0;
 }
 
-__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by, int32_t* step_idx) {
+// data parallel: append the all-gathered tokens of this step to the global history [step][world * width]
+__global__ void dp_unpack_kernel(const int32_t* __restrict__ recv, int n, int32_t* __restrict__ hist, int32_t* __restrict__ dp_step) {
+  const int s = *dp_step;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) hist[(size_t)s * n + i] = recv[i];
+  __syncthreads();
+  if (threadIdx.x == 0) *dp_step = s + 1;
+}
+int dp_unpack(const int32_t* recv, int n, int32_t* hist, int32_t* dp_step, cudaStream_t st) {
+  dp_unpack_kernel<<<1, 128, 0, st>>>(recv, n, hist, dp_step);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side KV page allocator
+// ------------------------------------------------------------------------------------------------
+__global__ void kv_reset_kernel(int32_t* __restrict__ kv_free, const int32_t* __restrict__ kv_order, int32_t* __restrict__ kv_state,
+                                int32_t* __restrict__ kv_npages, int total_pages, int max_batch) {
+  // stack top is the END of kv_free: page kv_order[0] must be popped first
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_pages; i += gridDim.x * blockDim.x) kv_free[total_pages - 1 - i] = kv_order[i];
+  if (blockIdx.x == 0) {
+    for (int b = threadIdx.x; b < max_batch; b += blockDim.x) kv_npages[b] = 0;
+    if (threadIdx.x == 0) { kv_state[0] = total_pages; kv_state[1] = 0; }
+  }
+}
+int kv_reset(int32_t* kv_free, const int32_t* kv_order, int32_t* kv_state, int32_t* kv_npages, int total_pages, int max_batch, cudaStream_t st) {
+  int blocks = (total_pages + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  if (blocks < 1) blocks = 1;
+  kv_reset_kernel<<<blocks, 256, 0, st>>>(kv_free, kv_order, kv_state, kv_npages, total_pages, max_batch);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// One thread: for page rank p = 0,1,..: every sequence that needs a p-th page and does not own one yet pops the stack.
+// need[b] = pages for `tokens[b]` tokens, clamped to the table row.
+__device__ void kv_reserve_serial(int32_t* kv_free, int32_t* kv_state, int32_t* kv_npages, int32_t* page_table, int pages_per_seq,
+                                  int page_tokens, int B, const int* s_tokens) {
+  int top = kv_state[0];
+  bool more = true;
+  for (int p = 0; more && p < pages_per_seq; ++p) {
+    more = false;
+    for (int b = 0; b < B; ++b) {
+      int need = (s_tokens[b] + page_tokens - 1) / page_tokens;
+      if (need > pages_per_seq) need = pages_per_seq;
+      if (need > p + 1) more = true;
+      if (need > p && kv_npages[b] == p) {
+        if (top <= 0) { kv_state[1] = 1; continue; }          // pool exhausted (unreachable behind the host-side capacity check)
+        page_table[(size_t)b * pages_per_seq + p] = kv_free[--top];
+        kv_npages[b] = p + 1;
+      }
+    }
+  }
+  kv_state[0] = top;
+}
+__global__ void kv_reserve_kernel(int32_t* kv_free, int32_t* kv_state, int32_t* kv_npages, int32_t* page_table, int pages_per_seq,
+                                  int page_tokens, int B, int S, const int32_t* __restrict__ left_pad) {
+  __shared__ int s_tokens[64];
+  if (threadIdx.x < B) s_tokens[threadIdx.x] = S - (left_pad ? left_pad[threadIdx.x] : 0);
+  __syncthreads();
+  if (threadIdx.x == 0) kv_reserve_serial(kv_free, kv_state, kv_npages, page_table, pages_per_seq, page_tokens, B, s_tokens);
+}
+int kv_reserve(int32_t* kv_free, int32_t* kv_state, int32_t* kv_npages, int32_t* page_table, int pages_per_seq, int page_tokens, int B, int S,
+               const int32_t* left_pad, cudaStream_t st) {
+  if (B > 64) { set_error("kv_reserve: batch %d > 64", B); return -1; }
+  kv_reserve_kernel<<<1, 64, 0, st>>>(kv_free, kv_state, kv_npages, page_table, pages_per_seq, page_tokens, B, S, left_pad);
+  VCLA_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void advance_seq_kernel(int32_t* seq_len, int B, int by, const int32_t* __restrict__ left_pad, int32_t* step_idx, int32_t* kv_free,
+                                   int32_t* kv_state, int32_t* kv_npages, int32_t* page_table, int pages_per_seq, int page_tokens) {
+  __shared__ int s_tokens[64];
   TraceScope trace(12);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
   pdl_wait();
   trace.dep();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) seq_len[b] += by;
+  const int b = threadIdx.x;
+  if (b < B) {
+    const int L = seq_len[b] + by - (left_pad ? left_pad[b] : 0);
+    seq_len[b] = L;
+    s_tokens[b] = L + 1;                 // the next token of this sequence is appended at index L
+  }
   if (step_idx != nullptr && b == 0) *step_idx += 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // fast path (every step but one in page_tokens): nobody crosses a page boundary
+    bool any = false;
+    for (int i = 0; i < B; ++i) {
+      int need = (s_tokens[i] + page_tokens - 1) / page_tokens;
+      if (need > pages_per_seq) need = pages_per_seq;
+      any |= need > kv_npages[i];
+    }
+    if (any) kv_reserve_serial(kv_free, kv_state, kv_npages, page_table, pages_per_seq, page_tokens, B, s_tokens);
+  }
 }
-int advance_seq(int32_t* seq_len, int B, int by, int32_t* step_idx, cudaStream_t st) {
-  VCLA_LAUNCH(advance_seq_kernel, dim3((B + 63) / 64), dim3(64), 0, st, seq_len, B, by, step_idx);
-  return 0;
-}
-
-__global__ void advance_seq_padded_kernel(int32_t* seq_len, int B, int S, const int32_t* left_pad, int32_t* step_idx) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) seq_len[b] += S - (left_pad ? left_pad[b] : 0);
-  if (step_idx != nullptr && b == 0) *step_idx += 1;
-}
-int advance_seq_padded(int32_t* seq_len, int B, int S, const int32_t* left_pad, int32_t* step_idx, cudaStream_t st) {
-  advance_seq_padded_kernel<<<(B + 63) / 64, 64, 0, st>>>(seq_len, B, S, left_pad, step_idx);
-  VCLA_CUDA_OK(cudaGetLastError());
+int advance_seq(int32_t* seq_len, int B, int by, const int32_t* left_pad, int32_t* step_idx, int32_t* kv_free, int32_t* kv_state,
+                int32_t* kv_npages, int32_t* page_table, int pages_per_seq, int page_tokens, cudaStream_t st) {
+  if (B > 64) { set_error("advance_seq: batch %d > 64", B); return -1; }
+  VCLA_LAUNCH(advance_seq_kernel, dim3(1), dim3(64), 0, st, seq_len, B, by, left_pad, step_idx, kv_free, kv_state, kv_npages, page_table,
+              pages_per_seq, page_tokens);
   return 0;
 }
 

@@ -3,19 +3,18 @@
 #include "../../include/vcla.h"
 #include "kernels.h"
 
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <list>
 #include <map>
 #include <string>
 #include <vector>
-
-namespace vcla {
-int rope_init(int max_pos, int head_dim, float theta);
-int argmax_scratch_init(int max_batch);
-}  // namespace vcla
 
 using namespace vcla;
 
@@ -53,12 +52,13 @@ struct TextLayer {
 };
 
 struct GraphKey {
-  int B; const void* tok_in; const void* logits; const void* tok_out; int n_steps = 1;
+  int B; const void* tok_in; const void* logits; const void* tok_out; int n_steps = 1; int dp = 0;
   bool operator<(const GraphKey& o) const {
     if (B != o.B) return B < o.B;
     if (tok_in != o.tok_in) return tok_in < o.tok_in;
     if (logits != o.logits) return logits < o.logits;
     if (n_steps != o.n_steps) return n_steps < o.n_steps;
+    if (dp != o.dp) return dp < o.dp;
     return tok_out < o.tok_out;
   }
 };
@@ -96,6 +96,18 @@ struct vcla_ctx {
   int pages_per_seq = 0, page_tokens = 64, total_pages = 0;
   size_t kv_layer_elems = 0;
   int32_t *page_table = nullptr, *seq_len = nullptr, *img_row_default = nullptr;
+  // device-side page allocator (elementwise.cu: kv_reset / kv_reserve / advance_seq): a stack of free physical pages, pages handed
+  // to sequences round-robin as they grow (so a sequence's pages are NOT contiguous), all stream-ordered and graph-capturable
+  int32_t *kv_free = nullptr, *kv_order = nullptr, *kv_state = nullptr, *kv_npages = nullptr;   // kv_state: [0] free count, [1] error flag
+  // RoPE tables and argmax scratch are per context (another context may use another theta / device / stream)
+  float *rope_cos = nullptr, *rope_sin = nullptr, *cand_val = nullptr; int32_t* cand_idx = nullptr;
+  int attn_persistent_mode = 1, attn_persistent_grid = 0;
+  // data parallel (vcla_nccl_init): per-step all-gather of the chosen tokens, captured inside the decode graph on a forked branch
+  ncclComm_t comm = nullptr; int dp_rank = 0, dp_world = 1, dp_width = 0; bool dp_active = false;
+  bool dp_on() const { return comm != nullptr && dp_active; }
+  int32_t *dp_send = nullptr, *dp_recv = nullptr, *dp_hist = nullptr, *dp_step = nullptr;
+  cudaStream_t dp_stream = nullptr; cudaEvent_t dp_fork = nullptr, dp_join = nullptr; bool dp_pending = false;
+  int64_t len_bound = 0;   // host-side upper bound of the cached tokens per sequence (prefill S + decode steps issued since)
   // vision activations
   bf16 *v_im2col = nullptr, *v_norm = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_ffn = nullptr;
   float *v_hidden = nullptr, *v_postln_f32 = nullptr;
@@ -119,6 +131,7 @@ struct vcla_ctx {
   // graphs
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int64_t> graph_launches;
+  std::list<GraphKey> graph_lru;          // most recently used first; bounded (kMaxGraphs) so a caller with ever-new buffers cannot grow it
   int64_t launches = 0;
   void* staging = nullptr; size_t staging_bytes = 0;
   void* trace_buf = nullptr; unsigned long long trace_cap = 0;
@@ -304,6 +317,14 @@ void layout_activations(vcla_ctx* c) {
   c->page_table = a_alloc<int32_t>(c, (size_t)g.max_batch * c->pages_per_seq);
   c->seq_len = a_alloc<int32_t>(c, g.max_batch);
   c->img_row_default = a_alloc<int32_t>(c, g.max_batch);
+  c->kv_free = a_alloc<int32_t>(c, (size_t)c->total_pages);
+  c->kv_order = a_alloc<int32_t>(c, (size_t)c->total_pages);
+  c->kv_state = a_alloc<int32_t>(c, 4);
+  c->kv_npages = a_alloc<int32_t>(c, g.max_batch);
+  c->rope_cos = a_alloc<float>(c, (size_t)(g.max_seq + 1) * 64);
+  c->rope_sin = a_alloc<float>(c, (size_t)(g.max_seq + 1) * 64);
+  c->cand_val = a_alloc<float>(c, Bp * kArgmaxChunks);
+  c->cand_idx = a_alloc<int32_t>(c, Bp * kArgmaxChunks);
 }
 
 // Split-K factor of a decode GEMM (row tiles of 128 x `splits` work units on 2 persistent CTAs per SM).  Measured on B200
@@ -312,7 +333,7 @@ void layout_activations(vcla_ctx* c) {
 int pick_splits(int n_out, int K) {
   const int tiles = (n_out + 127) / 128;
   const int kb = (K + 63) / 64;
-  const double slots = 2.0 * 148;
+  const double slots = 2.0 * num_sms();
   int best = 1;
   double best_score = 1e9;
   for (int want = 1; want <= 40; ++want) {
@@ -336,6 +357,41 @@ int pick_splits(int n_out, int K) {
 int count(vcla_ctx* c, int n = 1) { c->launches += n; return 0; }
 
 }  // namespace
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------------------------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+// NCCL is bound at run time (dlopen by soname: inside a torch process this resolves to the libnccl torch already loaded), so
+// libvcla.so itself has no link-time dependency on it and single-GPU users never touch it.
+static int nccl_api() {
+  if (g_nccl.lib) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_error("NCCL not found (dlopen libnccl.so.2: %s)", dlerror()); return -1; }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString) {
+    set_error("NCCL library lacks an expected symbol"); return -1;
+  }
+  g_nccl.lib = h;
+  return 0;
+}
+#define VCLA_NCCL_OK(expr)                                                                                   \
+  do {                                                                                                       \
+    ncclResult_t _r = (expr);                                                                                \
+    if (_r != ncclSuccess) { set_error("%s failed: %s", #expr, g_nccl.GetErrorString(_r)); return -1; }      \
+  } while (0)
+
 
 // =================================================================================================
 // C ABI
@@ -402,13 +458,15 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   layout_weights(c);
   layout_activations(c);
   for (int i = 0; i < g.t_layers; ++i) c->tl[i].kv = c->kv_arena + (size_t)i * c->kv_layer_elems;
-  // identity page table (sequence b owns pages [b*pps, (b+1)*pps)); kernels always go through the table
-  std::vector<int32_t> pt((size_t)g.max_batch * c->pages_per_seq);
-  for (size_t i = 0; i < pt.size(); ++i) pt[i] = (int32_t)i;
-  cudaMemcpy(c->page_table, pt.data(), pt.size() * 4, cudaMemcpyHostToDevice);
+  // page allocation order: physical pages 0,1,2,... are handed out in this order after every reset (vcla_kv_debug_shuffle permutes it)
+  std::vector<int32_t> order((size_t)c->total_pages);
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+  cudaMemcpy(c->kv_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice);
   std::vector<int32_t> two(g.max_batch, 2);
   cudaMemcpy(c->img_row_default, two.data(), two.size() * 4, cudaMemcpyHostToDevice);
-  if (rope_init(g.max_seq + 1, 128, g.rope_theta) || argmax_scratch_init(64) || attention_decode_init()) { vcla_destroy(c); return -1; }
+  if (const char* e = getenv("VCLA_ATTN_PERSISTENT")) c->attn_persistent_mode = atoi(e);
+  if (const char* e = getenv("VCLA_ATTN_PERSISTENT_GRID")) c->attn_persistent_grid = atoi(e);
+  if (rope_fill_tables(g.max_seq + 1, 128, g.rope_theta, c->rope_cos, c->rope_sin) || attention_init() || vcla_reset(c, nullptr)) { vcla_destroy(c); return -1; }
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("vcla_create: device error %s", cudaGetErrorString(cudaGetLastError())); vcla_destroy(c); return -1; }
   *out = c;
   return 0;
@@ -421,6 +479,12 @@ void vcla_destroy(vcla_ctx* c) {
   if (c->a_arena) cudaFree(c->a_arena);
   if (c->kv_arena) cudaFree(c->kv_arena);
   if (c->staging) cudaFree(c->staging);
+  c->graphs.clear();
+  if (c->comm) { cudaDeviceSynchronize(); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+  if (c->dp_send) cudaFree(c->dp_send);
+  if (c->dp_stream) cudaStreamDestroy(c->dp_stream);
+  if (c->dp_fork) cudaEventDestroy(c->dp_fork);
+  if (c->dp_join) cudaEventDestroy(c->dp_join);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); }
   delete c;
@@ -464,12 +528,16 @@ static int place_matrix(const Slot& s, const bf16* src, cudaStream_t st) {
   return 0;
 }
 
-int vcla_load_weight(vcla_ctx* c, const char* name, const void* src, int dtype, int on_device, vcla_stream stream) {
+int vcla_load_weight(vcla_ctx* c, const char* name, const void* src, int dtype, int64_t numel, int on_device, vcla_stream stream) {
   cudaStream_t st = (cudaStream_t)stream;
   auto it = c->slot_index.find(name);
   if (it == c->slot_index.end()) { set_error("vcla_load_weight: unknown tensor '%s'", name); return -1; }
   const Slot& s = c->slots[it->second];
   const size_t n = (size_t)s.rows * s.cols;
+  if (src == nullptr || numel != (int64_t)n) {
+    set_error("vcla_load_weight: '%s' holds %lld elements, the caller passed %lld (checkpoint / config shape mismatch)", name, (long long)n, (long long)numel);
+    return -1;
+  }
   const size_t esz = dtype == VCLA_F32 ? 4 : 2;
   if (dtype < 0 || dtype > 2) { set_error("vcla_load_weight: bad dtype"); return -1; }
   // staging: [raw source copy][bf16 contiguous]
@@ -539,6 +607,40 @@ int vcla_reset(vcla_ctx* c, vcla_stream stream) {
   VCLA_CUDA_OK(cudaMemsetAsync(c->seq_len, 0, (size_t)c->cfg.max_batch * 4, (cudaStream_t)stream));
   VCLA_CUDA_OK(cudaMemsetAsync(c->attn_counters, 0, (size_t)64 * c->cfg.t_heads * 4, (cudaStream_t)stream));
   VCLA_CUDA_OK(cudaMemsetAsync(c->step_idx, 0, 4, (cudaStream_t)stream));
+  // every page back on the free stack, no sequence owns any
+  if (kv_reset(c->kv_free, c->kv_order, c->kv_state, c->kv_npages, c->total_pages, c->cfg.max_batch, (cudaStream_t)stream)) return -1;
+  if (c->dp_step) VCLA_CUDA_OK(cudaMemsetAsync(c->dp_step, 0, 4, (cudaStream_t)stream));
+  c->len_bound = 0;
+  return 0;
+}
+
+int vcla_kv_debug_shuffle(vcla_ctx* c, uint32_t seed) {
+  // test hook: permute the order in which physical pages are handed out (Fisher-Yates over an LCG); takes effect at the next reset
+  std::vector<int32_t> order((size_t)c->total_pages);
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+  uint64_t x = 0x9E3779B97F4A7C15ull ^ seed;
+  for (size_t i = order.size(); i > 1; --i) {
+    x = x * 6364136223846793005ull + 1442695040888963407ull;
+    std::swap(order[i - 1], order[(size_t)((x >> 33) % i)]);
+  }
+  VCLA_CUDA_OK(cudaDeviceSynchronize());
+  VCLA_CUDA_OK(cudaMemcpy(c->kv_order, order.data(), order.size() * 4, cudaMemcpyHostToDevice));
+  return vcla_reset(c, nullptr);
+}
+
+int vcla_kv_read_pages(vcla_ctx* c, int32_t* table_host, int32_t* npages_host, int32_t* state_host) {
+  // synchronous copy of the page table [max_batch][pages_per_seq], the per-sequence page counts and {free pages, error flag}
+  VCLA_CUDA_OK(cudaDeviceSynchronize());
+  if (table_host) VCLA_CUDA_OK(cudaMemcpy(table_host, c->page_table, (size_t)c->cfg.max_batch * c->pages_per_seq * 4, cudaMemcpyDeviceToHost));
+  if (npages_host) VCLA_CUDA_OK(cudaMemcpy(npages_host, c->kv_npages, (size_t)c->cfg.max_batch * 4, cudaMemcpyDeviceToHost));
+  if (state_host) VCLA_CUDA_OK(cudaMemcpy(state_host, c->kv_state, 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int vcla_kv_geometry(const vcla_ctx* c, int* pages_per_seq, int* total_pages, int* page_tokens) {
+  if (!c) return -1;
+  if (pages_per_seq) *pages_per_seq = c->pages_per_seq;
+  if (total_pages) *total_pages = c->total_pages;
+  if (page_tokens) *page_tokens = c->page_tokens;
   return 0;
 }
 
@@ -621,13 +723,45 @@ static int swap_gemm(vcla_ctx* c, const bf16* W, int n_out, int K, const bf16* X
   count(c); return gemm_tc(g, st);
 }
 
+// ---- data parallel token exchange -------------------------------------------------------------------------------
+// One all-gather of this rank's `dp_width` token slots + append to the global history.  fork != 0: on the side stream, joined by
+// the next dp_wait() (the exchange is off the step's critical path: only the caller, not the next step, consumes it).
+static int dp_gather(vcla_ctx* c, cudaStream_t st, int fork) {
+  cudaStream_t gs = st;
+  if (fork) {
+    VCLA_CUDA_OK(cudaEventRecord(c->dp_fork, st));
+    VCLA_CUDA_OK(cudaStreamWaitEvent(c->dp_stream, c->dp_fork, 0));
+    gs = c->dp_stream;
+  }
+  VCLA_NCCL_OK(g_nccl.AllGather(c->dp_send, c->dp_recv, (size_t)c->dp_width, ncclInt32, c->comm, gs));
+  count(c); if (dp_unpack(c->dp_recv, c->dp_world * c->dp_width, c->dp_hist, c->dp_step, gs)) return -1;
+  if (fork) { VCLA_CUDA_OK(cudaEventRecord(c->dp_join, gs)); c->dp_pending = true; }
+  return 0;
+}
+static int dp_wait(vcla_ctx* c, cudaStream_t st) {
+  if (!c->dp_pending) return 0;
+  VCLA_CUDA_OK(cudaStreamWaitEvent(st, c->dp_join, 0));
+  c->dp_pending = false;
+  return 0;
+}
+
+// logits reduce + argmax (+ token exchange when data parallel)
+static int logits_argmax(vcla_ctx* c, int B, float* logits, int32_t* tok, const float* rstd, int fork, cudaStream_t st) {
+  const vcla_config& g = c->cfg;
+  if (c->dp_on() && dp_wait(c, st)) return -1;            // the previous step's exchange must have read dp_send before it is rewritten
+  count(c, 2);
+  if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok, c->tok_hist, c->step_idx, rstd, c->cand_val, c->cand_idx,
+                        c->dp_on() ? c->dp_send : nullptr, st)) return -1;
+  if (c->dp_on()) return dp_gather(c, st, fork);
+  return 0;
+}
+
 static int lm_head_last(vcla_ctx* c, int B, float* logits_dev, int32_t* tok_dev, cudaStream_t st) {
   // d_resid[B, T] holds the hidden state of the positions to score
   const vcla_config& g = c->cfg;
   count(c); if (dec_resid_norm(nullptr, 0, B, c->d_resid, B, g.t_hidden, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, g.t_hidden, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
-  count(c, 2);
-  return dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits_dev, g.t_vocab, tok_dev ? tok_dev : c->d_tok, c->tok_hist, c->step_idx, nullptr, st);
+  return logits_argmax(c, B, logits_dev, tok_dev ? tok_dev : c->d_tok, nullptr, 0, st);
 }
 
 int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, const int32_t* img_row, const int32_t* left_pad,
@@ -643,6 +777,8 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
   if (image_mode == VCLA_IMAGE_AT_HEAD && left_pad != nullptr) { set_error("prefill: left padding is not defined for the image_at_head layout"); return -1; }
   const int rows = B * S;
   if (vcla_reset(c, stream)) return -1;
+  // pages for the prompt's tokens (real tokens only: left padding is never cached)
+  count(c); if (kv_reserve(c->kv_free, c->kv_state, c->kv_npages, c->page_table, c->pages_per_seq, c->page_tokens, B, S, left_pad, st)) return -1;
   count(c); if (embed_tokens(ids, B, T, S, TH, c->embed, g.t_vocab, image_mode == VCLA_IMAGE_AT_HEAD ? 1 : 0, nq, c->resid, st)) return -1;
   if (image_mode != VCLA_TEXT_ONLY) {
     const int32_t* rs = (image_mode == VCLA_IMAGE_AT_HEAD || img_row == nullptr) ? c->img_row_default : img_row;
@@ -653,7 +789,7 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
     const TextLayer& L = c->tl[i];
     count(c); if (rmsnorm(c->resid, rows, TH, L.ln1, g.t_eps, c->xn, st)) return -1;
     if (gemm_bf16(c, c->xn, rows, TH, TH, L.wqkv, 3 * TH, TH, nullptr, ACT_NONE, c->qkv, 3 * TH, st)) return -1;
-    count(c); if (rope_and_cache(c->qkv, B, S, H, 128, g.rope_theta, L.kv, c->page_table, c->pages_per_seq, c->page_tokens, left_pad, pos_from_mask, st)) return -1;
+    count(c); if (rope_and_cache(c->qkv, B, S, H, 128, c->rope_cos, c->rope_sin, L.kv, c->page_table, c->pages_per_seq, c->page_tokens, left_pad, pos_from_mask, st)) return -1;
     AttnCall a; a.q = c->qkv; a.q_stride = 3 * TH; a.k0 = c->qkv + TH; a.v0 = c->qkv + 2 * TH; a.kv0_stride = 3 * TH; a.n0 = S;
     a.out = c->attn; a.o_stride = TH; a.B = B; a.H = H; a.Sq = S; a.HD = 128; a.scale = scale; a.causal = 1; a.kv_start = left_pad;
     count(c); if (attention_prefill(a, st)) return -1;
@@ -671,8 +807,14 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
   }
   count(c); if (gather_last_rows(c->resid, B, S, TH, c->d_resid, st)) return -1;
   if (lm_head_last(c, B, last_logits, next_tok, st)) return -1;
-  count(c); if (left_pad ? advance_seq_padded(c->seq_len, B, S, left_pad, c->step_idx, st) : advance_seq(c->seq_len, B, S, c->step_idx, st)) return -1;
+  // sequence lengths become S - pad; the page the first decoded token will be appended to is reserved here
+  count(c); if (advance_seq(c->seq_len, B, S, left_pad, c->step_idx, c->kv_free, c->kv_state, c->kv_npages, c->page_table, c->pages_per_seq, c->page_tokens, st)) return -1;
+  c->len_bound = S;
   return 0;
+}
+
+static int advance_and_reserve(vcla_ctx* c, int B, cudaStream_t st) {
+  return advance_seq(c->seq_len, B, 1, nullptr, c->step_idx, c->kv_free, c->kv_state, c->kv_npages, c->page_table, c->pages_per_seq, c->page_tokens, st);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -691,6 +833,7 @@ static int decode_enqueue_unfused(vcla_ctx* c, const int32_t* tok_in, int B, flo
     DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
     a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
     a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta;
+    a.rope_cos = c->rope_cos; a.rope_sin = c->rope_sin; a.persistent_mode = c->attn_persistent_mode; a.persistent_grid = c->attn_persistent_grid;
     { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
     count(c); if (attention_decode(a, st)) return -1;
     if (swap_gemm(c, L.wo, TH, TH, c->d_attn, B, c->sp_o, c->ws_o, st)) return -1;
@@ -701,8 +844,8 @@ static int decode_enqueue_unfused(vcla_ctx* c, const int32_t* tok_in, int B, flo
   }
   count(c); if (dec_resid_norm(c->ws_d, c->sp_d, B, c->d_resid, B, TH, c->final_norm, g.t_eps, c->d_xn, st)) return -1;
   if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
-  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, c->tok_hist, c->step_idx, nullptr, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, 1, c->step_idx, st)) return -1;
+  if (logits_argmax(c, B, logits, tok_out, nullptr, 1, st)) return -1;
+  count(c); if (advance_and_reserve(c, B, st)) return -1;
   return 0;
 }
 
@@ -725,6 +868,7 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
     DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = c->sp_qkv; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
     a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
     a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta; a.rstd = c->d_rstd;
+    a.rope_cos = c->rope_cos; a.rope_sin = c->rope_sin; a.persistent_mode = c->attn_persistent_mode; a.persistent_grid = c->attn_persistent_grid;
     // enough CTAs to cover the SMs for small batches; long contexts split so a CTA streams <= ~12 pages
     { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
     count(c); if (attention_decode(a, st)) return -1;
@@ -735,13 +879,13 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
     if (swap_gemm(c, L.wd, TH, F, c->d_h, B, c->sp_d, c->ws_d, st, &fr)) return -1;
   }
   if (swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st)) return -1;
-  count(c, 2); if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok_out, c->tok_hist, c->step_idx, c->d_rstd, st)) return -1;
-  count(c); if (advance_seq(c->seq_len, B, 1, c->step_idx, st)) return -1;
+  if (logits_argmax(c, B, logits, tok_out, c->d_rstd, 1, st)) return -1;
+  count(c); if (advance_and_reserve(c, B, st)) return -1;
   return 0;
 }
 
 static int decode_graph(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, int n_steps, cudaStream_t st) {
-  GraphKey key{B, tok_in, logits, tok_out, n_steps};
+  GraphKey key{B, tok_in, logits, tok_out, n_steps, c->dp_on() ? 1 : 0};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
     const int64_t before = c->launches;
@@ -750,6 +894,7 @@ static int decode_graph(vcla_ctx* c, const int32_t* tok_in, int B, float* logits
     VCLA_CUDA_OK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
     for (int i = 0; i < n_steps && rc == 0; ++i) rc = decode_enqueue(c, tok_in, B, logits, tok_out, c->cap_stream);
+    if (rc == 0 && c->dp_on()) rc = dp_wait(c, c->cap_stream);      // a captured graph must join its forked exchange branch
     cudaError_t e = cudaStreamEndCapture(c->cap_stream, &graph);
     if (rc != 0) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return -1; }
     if (e != cudaSuccess) { set_error("decode: graph capture failed: %s", cudaGetErrorString(e)); return -1; }
@@ -759,11 +904,39 @@ static int decode_graph(vcla_ctx* c, const int32_t* tok_in, int B, float* logits
     if (e != cudaSuccess) { set_error("decode: graph instantiate failed: %s", cudaGetErrorString(e)); return -1; }
     c->graph_launches[key] = c->launches - before;
     c->launches = before;  // capture enqueued nothing
+    // bounded cache: a caller that keeps passing fresh buffers evicts the least recently used graph instead of growing forever.
+    // (Evicting while an older launch of that graph may still be in flight needs the device to be idle first.)
+    constexpr size_t kMaxGraphs = 24;
+    if (c->graphs.size() >= kMaxGraphs) {
+      const GraphKey victim = c->graph_lru.back();
+      c->graph_lru.pop_back();
+      VCLA_CUDA_OK(cudaDeviceSynchronize());
+      cudaGraphExecDestroy(c->graphs[victim]);
+      c->graphs.erase(victim);
+      c->graph_launches.erase(victim);
+    }
     c->graphs[key] = exec;
+    c->graph_lru.push_front(key);
     it = c->graphs.find(key);
+  } else {
+    for (auto li = c->graph_lru.begin(); li != c->graph_lru.end(); ++li) {
+      if (!(*li < key) && !(key < *li)) { c->graph_lru.erase(li); break; }
+    }
+    c->graph_lru.push_front(key);
   }
   VCLA_CUDA_OK(cudaGraphLaunch(it->second, st));
   c->launches += c->graph_launches[key];
+  return 0;
+}
+
+// Every decode step appends one token per sequence: refuse the call instead of running past the context capacity (the kernels
+// index the page table, the RoPE table and the token history by the sequence length).
+static int decode_capacity(vcla_ctx* c, int n_steps) {
+  if (c->len_bound <= 0) { set_error("decode: no prefilled sequences (call vcla_prefill first)"); return -1; }
+  if (c->len_bound + n_steps > c->cfg.max_seq) {
+    set_error("decode: %lld cached tokens + %d steps exceed the context capacity max_seq=%d", (long long)c->len_bound, n_steps, c->cfg.max_seq);
+    return -1;
+  }
   return 0;
 }
 
@@ -771,8 +944,11 @@ int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, i
   cudaStream_t st = (cudaStream_t)stream;
   if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
   if (!tok_in || !tok_out) { set_error("decode: null token buffers"); return -1; }
-  if (!use_graph) return decode_enqueue(c, tok_in, B, logits, tok_out, st);
-  return decode_graph(c, tok_in, B, logits, tok_out, 1, st);
+  if (decode_capacity(c, 1)) return -1;
+  int rc = use_graph ? decode_graph(c, tok_in, B, logits, tok_out, 1, st) : decode_enqueue(c, tok_in, B, logits, tok_out, st);
+  if (rc == 0 && !use_graph && c->dp_on()) rc = dp_wait(c, st);
+  if (rc == 0) c->len_bound += 1;
+  return rc;
 }
 
 int vcla_decode_multi(vcla_ctx* c, int32_t* tok_inout, int B, int n_steps, vcla_stream stream) {
@@ -780,7 +956,75 @@ int vcla_decode_multi(vcla_ctx* c, int32_t* tok_inout, int B, int n_steps, vcla_
   // every chosen token is appended to the device-side history): amortises the gap between consecutive graph launches.
   if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
   if (!tok_inout || n_steps < 1 || n_steps > 64) { set_error("decode_multi: bad arguments"); return -1; }
-  return decode_graph(c, tok_inout, B, nullptr, tok_inout, n_steps, (cudaStream_t)stream);
+  if (decode_capacity(c, n_steps)) return -1;
+  const int rc = decode_graph(c, tok_inout, B, nullptr, tok_inout, n_steps, (cudaStream_t)stream);
+  if (rc == 0) c->len_bound += n_steps;
+  return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// data parallel: NCCL communicator owned by the context, token all-gather inside the decode graph
+// -------------------------------------------------------------------------------------------------
+int vcla_nccl_unique_id(uint8_t* out128) {
+  if (!out128) { set_error("vcla_nccl_unique_id: null"); return -1; }
+  if (nccl_api()) return -1;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  VCLA_NCCL_OK(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int vcla_nccl_init(vcla_ctx* c, const uint8_t* id128, int rank, int world, int width) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world || width < 1 || width > 64) { set_error("vcla_nccl_init: bad arguments"); return -1; }
+  if (c->comm) { set_error("vcla_nccl_init: context already has a communicator"); return -1; }
+  if (nccl_api()) return -1;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  VCLA_NCCL_OK(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  c->dp_rank = rank; c->dp_world = world; c->dp_width = width;
+  const size_t n_send = 64, n_recv = (size_t)world * 64, n_hist = (size_t)(c->cfg.max_seq + 2) * world * width;
+  VCLA_CUDA_OK(cudaMalloc(&c->dp_send, (n_send + n_recv + n_hist + 4) * 4));
+  VCLA_CUDA_OK(cudaMemset(c->dp_send, 0, (n_send + n_recv + n_hist + 4) * 4));
+  c->dp_recv = c->dp_send + n_send; c->dp_hist = c->dp_recv + n_recv; c->dp_step = c->dp_hist + n_hist;
+  VCLA_CUDA_OK(cudaStreamCreateWithFlags(&c->dp_stream, cudaStreamNonBlocking));
+  VCLA_CUDA_OK(cudaEventCreateWithFlags(&c->dp_fork, cudaEventDisableTiming));
+  VCLA_CUDA_OK(cudaEventCreateWithFlags(&c->dp_join, cudaEventDisableTiming));
+  // graphs captured before the communicator existed do not contain the exchange
+  VCLA_CUDA_OK(cudaDeviceSynchronize());
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  c->graphs.clear(); c->graph_launches.clear(); c->graph_lru.clear();
+  return 0;
+}
+
+int vcla_allgather_tokens(vcla_ctx* c, const int32_t* local_dev, int n, int32_t* all_dev, vcla_stream stream) {
+  if (!c || !c->comm) { set_error("vcla_allgather_tokens: call vcla_nccl_init first"); return -1; }
+  if (!local_dev || !all_dev || n < 1) { set_error("vcla_allgather_tokens: bad arguments"); return -1; }
+  VCLA_NCCL_OK(g_nccl.AllGather(local_dev, all_dev, (size_t)n, ncclInt32, c->comm, (cudaStream_t)stream));
+  return 0;
+}
+
+int vcla_dp_set_active(vcla_ctx* c, int on) {
+  // the exchange is part of prefill / decode only while active (every rank of the communicator must then make the same calls);
+  // a rank-local generate() on a context that owns a communicator runs with it off
+  if (!c) return -1;
+  if (on && !c->comm) { set_error("vcla_dp_set_active: call vcla_nccl_init first"); return -1; }
+  c->dp_active = on != 0;
+  return 0;
+}
+
+int vcla_dp_exchange(vcla_ctx* c, vcla_stream stream) {
+  // the exchange of one step without any compute: for a rank that holds no requests (global batch < world size)
+  if (!c || !c->comm) { set_error("vcla_dp_exchange: call vcla_nccl_init first"); return -1; }
+  return dp_gather(c, (cudaStream_t)stream, 0);
+}
+
+int vcla_read_history_dp(vcla_ctx* c, int32_t* dst_dev, int n_steps, vcla_stream stream) {
+  // [n_steps][world * width] int32: the tokens every rank chose at the prefill (row 0) and each decode step since
+  if (!c || !c->comm) { set_error("vcla_read_history_dp: call vcla_nccl_init first"); return -1; }
+  if (n_steps < 0 || n_steps > c->cfg.max_seq + 1) { set_error("vcla_read_history_dp: bad arguments"); return -1; }
+  VCLA_CUDA_OK(cudaMemcpyAsync(dst_dev, c->dp_hist, (size_t)n_steps * c->dp_world * c->dp_width * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -115,9 +115,13 @@ struct DecodeAttnCall {
   int B = 0, H = 0, HD = 0, kv_splits = 1;
   float scale = 1.f, rope_theta = 10000.f;
   const float* rstd = nullptr;         // [B] deferred RMSNorm scale of the QKV projection's input (null: 1)
+  const float* rope_cos = nullptr;     // [max_pos][HD/2] fp32 tables owned by the context
+  const float* rope_sin = nullptr;
+  int persistent_mode = 1;             // VCLA_ATTN_PERSISTENT (read once per context)
+  int persistent_grid = 0;             // VCLA_ATTN_PERSISTENT_GRID
 };
 int attention_decode(const DecodeAttnCall& c, cudaStream_t st);
-int attention_decode_init();   // sets the dynamic-smem attribute (call outside graph capture)
+int attention_init();          // sets the dynamic-smem attributes and reads the VCLA_ATTN_* switches once (call outside graph capture)
 
 // ------------------------------------------------------------------------------------------
 // normalisation / elementwise / data movement
@@ -142,9 +146,9 @@ int scatter_image_rows(const float* img, int B, int nq, int D, const int32_t* ro
 // prefill: RoPE q,k in place in the fused qkv buffer [B*S, 3T] and append k,v to the paged cache
 // left_pad[b] (nullable): rows s < left_pad[b] are padding (skipped); the cache index of row s is s - left_pad[b]; the RoPE
 // position is s - left_pad[b] when pos_from_mask (HF generate) else s (plain forward without position_ids)
-int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, float theta, bf16* kv_pages, const int32_t* page_table,
-                   int pages_per_seq, int page_tokens, const int32_t* left_pad, int pos_from_mask, cudaStream_t st);
-int advance_seq_padded(int32_t* seq_len, int B, int S, const int32_t* left_pad, int32_t* step_idx, cudaStream_t st);
+int rope_and_cache(bf16* qkv, int B, int S, int H, int HD, const float* rope_cos, const float* rope_sin, bf16* kv_pages,
+                   const int32_t* page_table, int pages_per_seq, int page_tokens, const int32_t* left_pad, int pos_from_mask,
+                   cudaStream_t st);
 int gather_last_rows(const float* hidden, int B, int S, int D, float* dst, cudaStream_t st);
 
 // decode consumers of split-K partials
@@ -154,16 +158,29 @@ int dec_resid_norm(const float* partial, int splits, int ws_rows, float* resid, 
 // h[b, j] = silu(sum_s p[s][b][g(j)]) * (sum_s p[s][b][u(j)])  with the [32 gate | 32 up] interleave
 int dec_silu_mul(const float* partial, int splits, int ws_rows, int B, int F, bf16* h, cudaStream_t st);
 // logits[b, :] = sum_s partial[s][b][:V] ; tok[b] = argmax (first max wins, like torch.argmax)
+// cand_val / cand_idx: [B][kArgmaxChunks] scratch owned by the context
+constexpr int kArgmaxChunks = 32;
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits,
-                      int32_t* tok, int32_t* history, const int32_t* step_idx, const float* rstd, cudaStream_t st);
+                      int32_t* tok, int32_t* history, const int32_t* step_idx, const float* rstd, float* cand_val,
+                      int32_t* cand_idx, int32_t* dp_send, cudaStream_t st);
+int dp_unpack(const int32_t* recv, int n, int32_t* hist, int32_t* dp_step, cudaStream_t st);
 // decode step entry: resid[b,:] = table[ids[b]] ; xw = bf16(resid * norm_w) ; rstd[b] = rsqrt(mean(resid^2) + eps)
 int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps,
               bf16* xw, float* rstd, cudaStream_t st);
-int advance_seq(int32_t* seq_len, int B, int by, int32_t* step_idx, cudaStream_t st);
-int rope_init(int max_pos, int head_dim, float theta);
-int argmax_scratch_init(int max_batch);
-const float* rope_cos_table();
-const float* rope_sin_table();
+// ---- device-side KV page allocator (stream-ordered, graph-capturable; one thread walks the <= 64 sequences, so the
+//      assignment is deterministic) ------------------------------------------------------------------------------
+// kv_state[0] = free pages, kv_state[1] = error flag (pool exhausted); kv_free = stack of free physical pages;
+// kv_npages[b] = pages owned by sequence b; page_table[b][i] = i-th page of sequence b.
+int kv_reset(int32_t* kv_free, const int32_t* kv_order, int32_t* kv_state, int32_t* kv_npages, int total_pages, int max_batch,
+             cudaStream_t st);
+// make sure sequence b owns pages for (S - left_pad[b]) tokens, b < B; pages are handed out round-robin over the sequences
+int kv_reserve(int32_t* kv_free, int32_t* kv_state, int32_t* kv_npages, int32_t* page_table, int pages_per_seq, int page_tokens,
+               int B, int S, const int32_t* left_pad, cudaStream_t st);
+// seq_len[b] += by - left_pad[b] ; *step_idx += 1 ; then reserve the page the NEXT token of every sequence will be appended to
+int advance_seq(int32_t* seq_len, int B, int by, const int32_t* left_pad, int32_t* step_idx, int32_t* kv_free, int32_t* kv_state,
+                int32_t* kv_npages, int32_t* page_table, int pages_per_seq, int page_tokens, cudaStream_t st);
+// fp32 RoPE tables [max_pos][head_dim/2], computed on the host the way HF does and uploaded to cos_dev / sin_dev
+int rope_fill_tables(int max_pos, int head_dim, float theta, float* cos_dev, float* sin_dev);
 
 // weights
 int fill_hash_normal(bf16* dst_bf16, float* dst_f32, int64_t n, uint32_t seed, float mul, float offset, cudaStream_t st);

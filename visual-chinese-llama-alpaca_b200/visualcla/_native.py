@@ -39,15 +39,24 @@ _SIGNATURES = [
     ("vcla_memory_bytes", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("vcla_weight_count", C.c_int, [_P]),
     ("vcla_weight_info", C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64 * 4), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    ("vcla_load_weight", C.c_int, [_P, C.c_char_p, _P, C.c_int, C.c_int, _P]),
+    ("vcla_load_weight", C.c_int, [_P, C.c_char_p, _P, C.c_int, C.c_int64, C.c_int, _P]),
     ("vcla_read_weight", C.c_int, [_P, C.c_char_p, _P, _P]),
     ("vcla_init_synthetic", C.c_int, [_P, C.c_uint32, _P]),
     ("vcla_reset", C.c_int, [_P, _P]),
+    ("vcla_kv_geometry", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("vcla_kv_read_pages", C.c_int, [_P, _P, _P, _P]),
+    ("vcla_kv_debug_shuffle", C.c_int, [_P, C.c_uint32]),
     ("vcla_vision_encode", C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     ("vcla_prefill", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P]),
     ("vcla_decode_step", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     ("vcla_decode_multi", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     ("vcla_read_history", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    ("vcla_nccl_unique_id", C.c_int, [_P]),
+    ("vcla_nccl_init", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
+    ("vcla_allgather_tokens", C.c_int, [_P, _P, C.c_int, _P, _P]),
+    ("vcla_dp_set_active", C.c_int, [_P, C.c_int]),
+    ("vcla_dp_exchange", C.c_int, [_P, _P]),
+    ("vcla_read_history_dp", C.c_int, [_P, _P, C.c_int, _P]),
     ("vcla_kernel_launches", C.c_int64, [_P, C.c_int]),
     ("vcla_read_stage", C.c_int, [_P, C.c_char_p, C.c_int, _P, _P]),
     ("vcla_op_gemm", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

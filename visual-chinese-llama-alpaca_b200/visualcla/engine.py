@@ -42,6 +42,8 @@ class Engine:
         self.nq = self.path_cfg["r_queries"]
         self.vocab = self.path_cfg["t_vocab"]
         self._names = None
+        self._table_cache = None
+        self._dp_tok = {}
 
     # ---- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -75,14 +77,27 @@ class Engine:
             self._names = out
         return self._names
 
+    def _table(self):
+        if getattr(self, "_table_cache", None) is None:
+            self._table_cache = {n: (s, k) for n, s, k in self.weight_table()}
+        return self._table_cache
+
     def load_weight(self, name: str, tensor: torch.Tensor):
+        """Copy one tensor (named as in the reference's state dict) into the arena.  The shape must be the slot's shape:
+        a checkpoint that disagrees with config.json is an error here, never an out-of-bounds read on the native side
+        (which checks the element count again)."""
+        table = self._table()
+        if name not in table:
+            raise KeyError(f"unknown tensor '{name}' for this model configuration")
         t = tensor.detach()
+        if tuple(t.shape) != tuple(table[name][0]):
+            raise ValueError(f"shape mismatch for {name}: checkpoint {tuple(t.shape)} vs model {tuple(table[name][0])}")
         if t.dtype not in _DTYPE:
             t = t.float()
         t = t.contiguous()
         on_dev = 1 if t.is_cuda else 0
         with torch.cuda.device(self.device):
-            N.check(self.lib.vcla_load_weight(self._ctx, name.encode(), N.ptr(t), _DTYPE[t.dtype], on_dev, self._stream()),
+            N.check(self.lib.vcla_load_weight(self._ctx, name.encode(), N.ptr(t), _DTYPE[t.dtype], t.numel(), on_dev, self._stream()),
                     f"vcla_load_weight({name})")
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True, prefix: str = ""):
@@ -164,6 +179,56 @@ class Engine:
                 N.check(self.lib.vcla_decode_multi(self._ctx, N.ptr(tok), B, k, self._stream()), "vcla_decode_multi")
                 left -= k
 
+    def token_buffer(self, n: int) -> torch.Tensor:
+        """Persistent int32 (n,) device buffer per batch size: its address keys the captured decode graphs."""
+        if n not in self._dp_tok:
+            with torch.inference_mode(False):
+                self._dp_tok[n] = torch.zeros(n, dtype=torch.int32, device=self.device)
+        return self._dp_tok[n]
+
+    # ---- data parallel: communicator + in-graph token exchange (include/vcla.h, "data parallel") -------------
+    dp_width = 0
+
+    def dp_init(self, group=None):
+        """Create this context's NCCL communicator once (collective over the process group): rank 0's ncclUniqueId is
+        shipped through torch.distributed, the communicator itself belongs to the native context."""
+        import torch.distributed as dist
+        if self.dp_width:
+            return
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            N.check(self.lib.vcla_nccl_unique_id(N.ptr(uid)), "vcla_nccl_unique_id")
+        uid_d = uid.to(self.device)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(uid_d, src=src, group=group)
+        uid = uid_d.cpu()
+        width = min(64, self.max_batch)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_nccl_init(self._ctx, N.ptr(uid), rank, world, width), "vcla_nccl_init")
+        self.dp_width, self.dp_world = width, world
+
+    def dp_set_active(self, on: bool):
+        N.check(self.lib.vcla_dp_set_active(self._ctx, 1 if on else 0), "vcla_dp_set_active")
+
+    def dp_idle_exchange(self):
+        """A rank that holds no requests (global batch < world) still has to enter every step's all-gather."""
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_dp_exchange(self._ctx, self._stream()), "vcla_dp_exchange")
+
+    def allgather_tokens(self, local: torch.Tensor) -> torch.Tensor:
+        out = torch.empty(self.dp_world * local.numel(), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_allgather_tokens(self._ctx, N.ptr(local), local.numel(), N.ptr(out), self._stream()), "vcla_allgather_tokens")
+        return out
+
+    def read_history_dp(self, n_steps: int) -> torch.Tensor:
+        """(n_steps, world * dp_width) int32 CUDA tensor: every rank's tokens of the prefill (row 0) and each decode step."""
+        out = torch.empty(n_steps, self.dp_world * self.dp_width, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_read_history_dp(self._ctx, N.ptr(out), n_steps, self._stream()), "vcla_read_history_dp")
+        return out
+
     def read_history(self, B: int, n_steps: int) -> torch.Tensor:
         """(n_steps, B) int32 CUDA tensor: tokens chosen by the prefill (row 0) and each decode step since."""
         out = torch.empty(n_steps, B, dtype=torch.int32, device=self.device)
@@ -174,6 +239,27 @@ class Engine:
     def reset(self):
         with torch.cuda.device(self.device):
             N.check(self.lib.vcla_reset(self._ctx, self._stream()), "vcla_reset")
+
+    # ---- paged KV cache introspection ---------------------------------------------------------
+    def kv_geometry(self) -> Tuple[int, int, int]:
+        """(pages per sequence, pages in the pool, tokens per page)."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        N.check(self.lib.vcla_kv_geometry(self._ctx, C.byref(a), C.byref(b), C.byref(c)), "vcla_kv_geometry")
+        return a.value, b.value, c.value
+
+    def kv_pages(self):
+        """-> (page_table (max_batch, pages_per_seq) int32, pages owned per sequence (max_batch,), free pages, exhausted flag)."""
+        pps, _total, _pt = self.kv_geometry()
+        table = torch.zeros(self.max_batch, pps, dtype=torch.int32)
+        owned = torch.zeros(self.max_batch, dtype=torch.int32)
+        state = torch.zeros(2, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_kv_read_pages(self._ctx, N.ptr(table), N.ptr(owned), N.ptr(state)), "vcla_kv_read_pages")
+        return table, owned, int(state[0]), int(state[1])
+
+    def kv_debug_shuffle(self, seed: int):
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_kv_debug_shuffle(self._ctx, seed), "vcla_kv_debug_shuffle")
 
     def kernel_launches(self, reset: bool = False) -> int:
         return int(self.lib.vcla_kernel_launches(self._ctx, 1 if reset else 0))

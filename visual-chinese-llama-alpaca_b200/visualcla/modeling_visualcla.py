@@ -257,13 +257,23 @@ class VisualCLAModel:
             vc = json.load(f)
             config.vision_config = vc.get("vision_config", vc) if "hidden_size" not in vc else vc
         model = cls(config, device=default_device, torch_dtype=torch_dtype, **kwargs)
-        model._engine.init_synthetic(0)   # resampler + projector: fresh init, as in the reference
+        eng = model._engine
+        eng.init_synthetic(0)   # resampler + projector: fresh init, as in the reference
+        known = {n for n, _s, _k in eng.weight_table()}
+        seen = set()
         for k, v in _iter_checkpoint(text_model_name_or_path):
             if "rotary_emb.inv_freq" not in k:
-                model._engine.load_weight("text_model." + k, v)
+                eng.load_weight("text_model." + k, v); seen.add("text_model." + k)
         for k, v in _iter_checkpoint(vision_model_name_or_path):
-            if k.startswith("vision_model.") and "position_ids" not in k:
-                model._engine.load_weight("vision_model." + k, v)
+            # a full CLIPModel checkpoint also carries the text tower / projections: only the vision tower is on the path
+            name = "vision_model." + k
+            if name in known:
+                eng.load_weight(name, v); seen.add(name)
+        # only the resampler and the projector may keep their fresh initialisation: a missing shard or a renamed key must
+        # not leave LLaMA / CLIP layers at random weights
+        missing = sorted(n for n in known - seen if n.startswith(("text_model.", "vision_model.")))
+        if missing:
+            raise RuntimeError(f"base checkpoints lack {len(missing)} tensors of the text/vision towers, e.g. {missing[:4]}")
         return model
 
     def save_merged_pretrained(self, output_dir: str):
