@@ -80,6 +80,10 @@ def case_tiny(visualcla, name, seed, batch, t_text, n_new):
     model.image_at_head = True
     out = model(input_ids=ids, pixel_values=pixels, attention_mask=mask, labels=ids, return_dict=True)
     logits_head = out.logits
+    loss_head = out.loss                      # labels get -100 over the image block (ref: modeling_visualcla.py:313-315)
+    labels_masked = ids.clone()
+    labels_masked[:, 3::3] = -100             # some ignored text positions as well
+    loss_head_masked = model(input_ids=ids, pixel_values=pixels, attention_mask=mask, labels=labels_masked, return_dict=True).loss
 
     # placeholder layout (loader default, ref: modeling_utils.py:134)
     nq = cfg.r_queries
@@ -88,9 +92,10 @@ def case_tiny(visualcla, name, seed, batch, t_text, n_new):
     model.tokenizer = types.SimpleNamespace(img_start_token_id=s0, img_end_token_id=s1, img_token_id=s3)
     out_ph = model(input_ids=ids_ph, pixel_values=pixels, attention_mask=torch.ones_like(ids_ph), return_dict=True)
     logits_ph = out_ph.logits
+    loss_ph = model(input_ids=ids_ph, pixel_values=pixels, attention_mask=torch.ones_like(ids_ph), labels=ids_ph, return_dict=True).loss
 
     # text only
-    out_txt = model(input_ids=ids, pixel_values=None, attention_mask=mask, return_dict=True)
+    out_txt = model(input_ids=ids, pixel_values=None, attention_mask=mask, labels=ids, return_dict=True)
 
     # greedy generate, eos disabled, returns only new tokens (ref: modeling_visualcla.py:333-392)
     from transformers import GenerationConfig
@@ -112,6 +117,8 @@ def case_tiny(visualcla, name, seed, batch, t_text, n_new):
         vit_out=vit.numpy(), post_ln=post.numpy(), resampler_out=res.numpy(), projector_out=proj.numpy(),
         logits_at_head=logits_head.numpy(), logits_placeholder=logits_ph.numpy(), logits_text_only=out_txt.logits.numpy(),
         gen_tokens=gen_tokens.numpy(), gen_logits=gen_logits.float().numpy(),
+        loss_at_head=loss_head.numpy(), labels_masked=labels_masked.numpy(), loss_at_head_masked=loss_head_masked.numpy(),
+        loss_placeholder=loss_ph.numpy(), loss_text_only=out_txt.loss.numpy(),
     )
     print(f"[golden] {name}: logits {tuple(logits_head.shape)} gen {tuple(gen_tokens.shape)} "
           f"max|logit| {logits_head.abs().max():.3f} layout diff {float((logits_head - logits_ph).abs().max()):.2e}")
@@ -197,7 +204,26 @@ def case_host_logic(visualcla):
     logits = torch.randn(3, 500, generator=g) * 3.0
     tfs = mu.TailFreeLogitsWarper(tfs=0.9)(None, logits.clone())
     topa = mu.TopALogitsWarper(top_a=0.2)(None, logits.clone())
-    np.savez_compressed(os.path.join(OUT, "samplers.npz"), logits=logits.numpy(), tfs_0p9=tfs.numpy(), top_a_0p2=topa.numpy())
+    # the logits-processor chain HF's generate() builds for the reference's DEFAULT_GENERATION_CONFIG (ref: modeling_utils.py:36-47:
+    # repetition_penalty 1.1, no_repeat_ngram_size 15, temperature 0.5, top_k 40, top_p 0.9), applied to a generated-token history
+    # (with inputs_embeds the processors only ever see the NEW tokens).  Two histories: one with a repeated n-gram (n = 3 so that a
+    # short history exercises the ban) and the default n = 15.
+    from transformers.generation import logits_process as lp
+    V = 2000
+    big = torch.randn(4, V, generator=g) * 4.0
+    hist = torch.randint(0, V, (4, 24), generator=g)
+    hist[0, 10:12] = hist[0, 2:4]; hist[0, 22:24] = hist[0, 2:4]     # row 0: "... a b X ... a b Y ... a b" -> X and Y banned at n = 3
+    hist[1, 20:24] = hist[1, 5:9]
+    chain = {}
+    for n_gram in (3, 15):
+        x = big.clone()
+        x = lp.RepetitionPenaltyLogitsProcessor(penalty=1.1)(hist, x); chain[f"n{n_gram}_rep"] = x.clone()
+        x = lp.NoRepeatNGramLogitsProcessor(n_gram)(hist, x); chain[f"n{n_gram}_ngram"] = x.clone()
+        x = lp.TemperatureLogitsWarper(0.5)(hist, x); chain[f"n{n_gram}_temp"] = x.clone()
+        x = lp.TopKLogitsWarper(top_k=40, min_tokens_to_keep=1)(hist, x); chain[f"n{n_gram}_topk"] = x.clone()
+        x = lp.TopPLogitsWarper(top_p=0.9, min_tokens_to_keep=1)(hist, x); chain[f"n{n_gram}_topp"] = x.clone()
+    np.savez_compressed(os.path.join(OUT, "samplers.npz"), logits=logits.numpy(), tfs_0p9=tfs.numpy(), top_a_0p2=topa.numpy(),
+                        chain_logits=big.numpy(), chain_history=hist.numpy(), **{k: v.numpy() for k, v in chain.items()})
     print(f"[golden] host logic: {len(cases)} prompts; tfs keeps {int(torch.isfinite(tfs).sum())}, top_a keeps {int(torch.isfinite(topa).sum())}")
 
 

@@ -523,6 +523,21 @@ def forward_logits(w, cfg: PathConfig, input_ids, pixel_values, image_at_head: b
     return llama_forward(w, cfg, x)
 
 
+def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor, n_image_rows: int = 0) -> torch.Tensor:
+    """forward(labels=...).loss.  In the image_at_head layout the reference widens the labels with -100 over the image block
+    after the first label (ref: modeling_visualcla.py:313-315); LlamaForCausalLM then shifts by one and averages the
+    cross-entropy over the positions whose label is not -100 (HF:models/llama/modeling_llama.py:489-491 ->
+    HF:loss/loss_utils.py ForCausalLMLoss: logits upcast to fp32, labels padded with -100 and shifted, mean reduction)."""
+    if n_image_rows > 0:
+        fill = torch.full((labels.shape[0], n_image_rows), -100, dtype=labels.dtype)
+        labels = torch.cat([labels[:, :1], fill, labels[:, 1:]], dim=1)
+    lg = logits.float()[:, :-1].reshape(-1, logits.shape[-1])
+    tgt = labels[:, 1:].reshape(-1)
+    keep = tgt != -100
+    logp = torch.log_softmax(lg[keep], dim=-1)
+    return -(logp.gather(1, tgt[keep].unsqueeze(1)).squeeze(1)).mean()
+
+
 def generate_greedy(w, cfg: PathConfig, input_ids, pixel_values, max_new_tokens: int,
                     image_at_head: bool = True, forced_tokens: Optional[torch.Tensor] = None,
                     return_logits: bool = True, left_pad: Optional[torch.Tensor] = None):

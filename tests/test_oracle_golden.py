@@ -55,6 +55,21 @@ def test_stages_and_logits(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_loss_against_reference(golden_dir, name):
+    """forward(labels=...).loss of the unmodified reference (incl. its -100 fill over the image block, ref
+    modeling_visualcla.py:313-315) vs the oracle's restatement, in all three layouts and with ignored label positions."""
+    g, cfg = _load(golden_dir, name)
+    w = O.make_weights(cfg, int(g["seed"]))
+    px, ids = torch.from_numpy(g["pixel_values"]), torch.from_numpy(g["input_ids"])
+    lg = O.forward_logits(w, cfg, ids, px, image_at_head=True)
+    assert abs(float(O.causal_lm_loss(lg, ids, cfg.r_queries)) - float(g["loss_at_head"])) <= 1e-4
+    assert abs(float(O.causal_lm_loss(lg, torch.from_numpy(g["labels_masked"]), cfg.r_queries)) - float(g["loss_at_head_masked"])) <= 1e-4
+    ids_ph = torch.from_numpy(g["input_ids_placeholder"])
+    assert abs(float(O.causal_lm_loss(O.forward_logits(w, cfg, ids_ph, px, image_at_head=False), ids_ph)) - float(g["loss_placeholder"])) <= 1e-4
+    assert abs(float(O.causal_lm_loss(O.forward_logits(w, cfg, ids, None), ids)) - float(g["loss_text_only"])) <= 1e-4
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_greedy_generate(golden_dir, name):
     g, cfg = _load(golden_dir, name)
     w = O.make_weights(cfg, int(g["seed"]))

@@ -18,8 +18,20 @@ import visualcla_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-STAGE_TOL = 3e-2      # relative to the stage's max |value|
-LOGIT_TOL = 4e-2      # relative to max |logit|
+# Gates = ~1.5x the error measured on B200 (profiles/r2_parity_measured.json; every run appends its measured values to
+# $VCLA_PARITY_LOG when set).  north_star's "1e-3" is below what ANY bf16 path reaches against an fp32 oracle -- see
+# test_7b_error_not_worse_than_hf_bf16, which measures HF's own bf16 path on the same GPU, weights and inputs.
+STAGE_TOL = {"vit_out": 3e-2, "post_ln": 3e-2, "resampler_out": 3e-2, "projector_out": 3e-2}      # relative to the stage's max |value|
+LOGIT_TOL = 1.5e-2    # relative to max |logit|
+LOSS_TOL = 5e-3       # absolute, cross-entropy in nats
+
+
+def _record(key, value):
+    path = os.environ.get("VCLA_PARITY_LOG")
+    if path:
+        import json
+        with open(path, "a") as f:
+            f.write(json.dumps({"key": key, "value": value}) + "\n")
 
 
 def _rel_err(a, b):
@@ -78,20 +90,29 @@ def test_tiny_against_reference_golden(golden_dir, name):
     out = m.forward(input_ids=ids, pixel_values=px, attention_mask=torch.ones_like(ids), labels=ids)
     for st in ("vit_out", "post_ln", "resampler_out", "projector_out"):
         e = _rel_err(m._engine.read_stage(st, B), g[st])
-        assert e <= STAGE_TOL, f"{st}: rel err {e:.3e}"
+        _record(f"{name}.{st}", e)
+        assert e <= STAGE_TOL[st], f"{st}: rel err {e:.3e}"
     e = _rel_err(out.logits, g["logits_at_head"])
+    _record(f"{name}.logits_at_head", e)
     assert e <= LOGIT_TOL, f"logits_at_head rel err {e:.3e}"
-    assert _rel_err(m.embed_images(px), g["projector_out"]) <= STAGE_TOL      # tg-webui entry point (embed_images)
+    assert _rel_err(m.embed_images(px), g["projector_out"]) <= STAGE_TOL["projector_out"]      # tg-webui entry point (embed_images)
+    # forward(labels=...).loss vs the reference's own loss: -100 fill over the image block (ref :313-315), ignored labels
+    _record(f"{name}.loss_at_head", abs(float(out.loss) - float(g["loss_at_head"])))
+    assert abs(float(out.loss) - float(g["loss_at_head"])) <= LOSS_TOL
+    lm = m.forward(input_ids=ids, pixel_values=px, attention_mask=torch.ones_like(ids), labels=torch.from_numpy(g["labels_masked"]).cuda()).loss
+    assert abs(float(lm) - float(g["loss_at_head_masked"])) <= LOSS_TOL
     # placeholder layout (what get_model_and_tokenizer_and_processor configures)
     s0, s1, _, s3 = O.special_ids(cfg)
     m.image_at_head = False
     m.tokenizer = types.SimpleNamespace(img_start_token_id=s0, img_end_token_id=s1, img_token_id=s3)
     ids_ph = torch.from_numpy(g["input_ids_placeholder"]).cuda()
-    out_ph = m.forward(input_ids=ids_ph, pixel_values=px, attention_mask=torch.ones_like(ids_ph))
+    out_ph = m.forward(input_ids=ids_ph, pixel_values=px, attention_mask=torch.ones_like(ids_ph), labels=ids_ph)
     assert _rel_err(out_ph.logits, g["logits_placeholder"]) <= LOGIT_TOL
     assert torch.equal(out_ph.logits, out.logits), "layout equivalence (SURVEY 4-iv) must be bit-exact on the device too"
-    out_txt = m.forward(input_ids=ids, pixel_values=None, attention_mask=torch.ones_like(ids))
+    assert abs(float(out_ph.loss) - float(g["loss_placeholder"])) <= LOSS_TOL
+    out_txt = m.forward(input_ids=ids, pixel_values=None, attention_mask=torch.ones_like(ids), labels=ids)
     assert _rel_err(out_txt.logits, g["logits_text_only"]) <= LOGIT_TOL
+    assert abs(float(out_txt.loss) - float(g["loss_text_only"])) <= LOSS_TOL
     # greedy generation: only the new tokens come back
     n = g["gen_tokens"].shape[1]
     m.image_at_head = True
@@ -137,6 +158,7 @@ def _run_vs_oracle(cfg, seed, B, T, n_new, max_seq, logit_tol=LOGIT_TOL, weights
     scale = o_log.abs().max().item()
     err = (d_log.cpu() - o_log).abs().max().item() / scale
     nbad, ndec, ntot = _margin_ok_tokens(d_tok.long(), o_tok, o_log, logit_tol * scale)
+    _record(f"vs_oracle.hidden{cfg.t_hidden}.layers{cfg.t_layers}.B{B}.T{T}.steps{n_new}", err)
     return m, err, nbad, ndec, ntot, o_tok, o_log
 
 
@@ -359,18 +381,106 @@ def test_placeholder_errors_and_eos():
     assert torch.equal(samp, free)
 
 
-@pytest.mark.skipif(os.environ.get("VCLA_SKIP_7B") == "1", reason="VCLA_SKIP_7B=1")
+# ---------------------------------------------------------------------------------------------------------------
+# Real VisualCLA-7B widths (BASELINE.json configs).  The oracle gets the device's own bf16 weights (vcla_read_weight).
+# ---------------------------------------------------------------------------------------------------------------
+skip7b = pytest.mark.skipif(os.environ.get("VCLA_SKIP_7B") == "1", reason="VCLA_SKIP_7B=1")
+
+
+def _dl(m):
+    return {k: v.float() for k, v in m.state_dict().items()}
+
+
+def _7b_case(tag, B, T, n_new, max_seq, t_layers=None):
+    cfg = O.PathConfig() if t_layers is None else O.PathConfig(t_layers=t_layers)
+    print(f"[7B parity {tag}] oracle host threads: {O.pick_threads()}")
+    m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 0, B, T, n_new, max_seq, weights=_dl)
+    print(f"[7B parity {tag}] teacher-forced logits rel err {err:.3e}; decisive tokens {ndec}/{ntot}, mismatches {nbad}")
+    eng = m._engine
+    try:
+        assert err <= LOGIT_TOL
+        assert nbad == 0
+    finally:
+        eng.close()
+
+
+@skip7b
 def test_config1_7b_logit_parity_gate():
-    """BASELINE config 1: real VisualCLA-7B widths, 1 image + 32-token prompt (S=96), greedy decode, oracle = fp32 on CPU.
-    The oracle gets the device's own bf16 weights (vcla_read_weight), generated by the hash generator."""
-    n_new = int(os.environ.get("VCLA_7B_STEPS", "24"))
+    """BASELINE configs[0]: 1 image + 32-token prompt (S=96), the full 64 greedy tokens teacher-forced, oracle = fp32 on CPU."""
+    _7b_case("cfg1", 1, 32, int(os.environ.get("VCLA_7B_STEPS", "64")), 256)
+
+
+@skip7b
+def test_config2_7b_batch8():
+    """BASELINE configs[1] shapes at full depth: B=8, S=128 (BN=16 decode tiles, 4-way split-KV one-shot decode attention)."""
+    _7b_case("cfg2", 8, 64, 6, 128 + 256 + 1)
+
+
+@skip7b
+def test_config3_7b_batch32():
+    """BASELINE configs[2] shapes: B=32, T=128 (S=192): BN=32 decode tiles, persistent decode-attention kernel (32 x 32 items).
+    Full widths, 8 of the 32 LLaMA layers by default (every kernel / tile / split choice depends on widths and batch, not on
+    depth; depth is covered by cfg1/cfg2) -- VCLA_PARITY_FULL_DEPTH=1 runs all 32."""
+    _7b_case("cfg3", 32, 128, 5, 192 + 256 + 1, None if os.environ.get("VCLA_PARITY_FULL_DEPTH") == "1" else 8)
+
+
+@skip7b
+def test_config5_7b_long_context():
+    """BASELINE configs[4] shapes: B=16, T=1024 (S=1088): kv_splits=4 decode attention over 17+ pages, 17 KV tiles of causal
+    prefill attention.  Full widths, 8 LLaMA layers by default (see cfg3)."""
+    _7b_case("cfg5", 16, 1024, 4, 1088 + 512 + 1, None if os.environ.get("VCLA_PARITY_FULL_DEPTH") == "1" else 8)
+
+
+@skip7b
+def test_7b_error_not_worse_than_hf_bf16():
+    """north_star asks for logits "within 1e-3 bf16"; a bf16 rounding is 2^-9 = 2e-3, so the honest bar is HF's own bf16 path:
+    the very HF classes the reference calls (CLIPVisionModel, LlamaForCausalLM; Resampler = the oracle's torch restatement), in
+    bf16 on this GPU, with the same weights and inputs.  err(this repo vs fp32 oracle) must not exceed 1.1 x err(HF-bf16 vs
+    fp32 oracle)."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.clip.modeling_clip import CLIPVisionConfig, CLIPVisionModel
     cfg = O.PathConfig()
-    print(f"[7B parity] oracle host threads: {O.pick_threads()}")
-
-    def dl(m):
-        return {k: v.float() for k, v in m.state_dict().items()}
-
-    m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 0, 1, 32, n_new, 256, weights=dl)
-    print(f"[7B parity] teacher-forced logits rel err {err:.3e}; decisive tokens {ndec}/{ntot}, mismatches {nbad}")
-    assert err <= LOGIT_TOL
-    assert nbad == 0
+    m = _model(cfg, 0, 1, 256)
+    sd = m.state_dict()                                       # bf16 matrices / fp32 vectors, reference state-dict names
+    px, ids = O.make_inputs(cfg, 1, 32, seed=77)
+    m.image_at_head = True
+    ours = m.forward(input_ids=ids.cuda(), pixel_values=px.cuda(), attention_mask=torch.ones_like(ids).cuda(), labels=ids.cuda()).logits.float().cpu()
+    m._engine.close()
+    w32 = {k: v.float() for k, v in sd.items()}
+    ref = O.forward_logits(w32, cfg, ids, px, image_at_head=True)
+    del w32
+    dt = torch.bfloat16
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dt)
+    try:
+        with torch.device("cuda"):
+            llama = LlamaForCausalLM(LlamaConfig(vocab_size=cfg.t_vocab, hidden_size=cfg.t_hidden, intermediate_size=cfg.t_ffn,
+                                                 num_hidden_layers=cfg.t_layers, num_attention_heads=cfg.t_heads, num_key_value_heads=cfg.t_heads,
+                                                 rms_norm_eps=cfg.t_eps, rope_theta=cfg.rope_theta, max_position_embeddings=2048,
+                                                 tie_word_embeddings=False, pad_token_id=0, bos_token_id=1, eos_token_id=2)).eval()
+            clip = CLIPVisionModel(CLIPVisionConfig(hidden_size=cfg.v_hidden, intermediate_size=cfg.v_ffn, num_hidden_layers=cfg.v_layers,
+                                                    num_attention_heads=cfg.v_heads, image_size=cfg.v_image, patch_size=cfg.v_patch,
+                                                    hidden_act="quick_gelu", layer_norm_eps=cfg.v_eps)).eval()
+    finally:
+        torch.set_default_dtype(old)
+    tsd = {k[len("text_model."):]: v for k, v in sd.items() if k.startswith("text_model.")}
+    vsd = {k[len("vision_model."):]: v for k, v in sd.items() if k.startswith("vision_model.")}
+    miss = llama.load_state_dict(tsd, strict=False)
+    assert not [k for k in miss.missing_keys if "rotary" not in k] and not miss.unexpected_keys, miss
+    miss = clip.load_state_dict(vsd, strict=False)
+    assert not [k for k in miss.missing_keys if "position_ids" not in k] and not miss.unexpected_keys, miss
+    wr = {k: v.cuda().to(dt) for k, v in sd.items() if k.startswith(("visual_resampler.", "image_projection_layer."))}
+    with torch.no_grad():
+        emb = llama.get_input_embeddings()(ids.cuda())
+        vit = clip(pixel_values=px.cuda().to(dt))[0]
+        post = clip.vision_model.post_layernorm(vit)
+        img = O.project(wr, O.resampler_forward(wr, cfg, post)).to(dt)
+        x = torch.cat([emb[:, :2], img, emb[:, 2:]], dim=1)
+        hf = llama(inputs_embeds=x, attention_mask=torch.ones(x.shape[:2], dtype=torch.long, device="cuda")).logits.float().cpu()
+    scale = ref.abs().max().item()
+    e_ours, e_hf = (ours - ref).abs().max().item() / scale, (hf - ref).abs().max().item() / scale
+    rms_ours, rms_hf = (ours - ref).pow(2).mean().sqrt().item() / scale, (hf - ref).pow(2).mean().sqrt().item() / scale
+    print(f"[7B vs HF-bf16] max rel err: this repo {e_ours:.3e}, HF bf16 {e_hf:.3e}; rms: {rms_ours:.3e} vs {rms_hf:.3e}")
+    _record("hf_bf16_comparison", {"ours_max": e_ours, "hf_bf16_max": e_hf, "ours_rms": rms_ours, "hf_bf16_rms": rms_hf})
+    assert e_ours <= 1.1 * e_hf, f"this repo {e_ours:.3e} vs HF bf16 {e_hf:.3e}"
+    assert e_ours <= LOGIT_TOL

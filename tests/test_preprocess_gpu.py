@@ -2,10 +2,8 @@
 oracle/clip_preprocess_oracle.py: integer work, so the bar is bit-exact (float32 result identical; f16/bf16 = the
 round-to-nearest cast of it).
 
-Status: the per-thread code of both kernels is replayed on the host bit for bit by tests/test_preprocess_core_cpu.py, but
-the round's GPU budget was spent before these launches could be run on a B200 once.  Until that first device run the
-tests are marked xfail(strict=False): an XPASS is the evidence that the device path matches, an XFAIL cannot turn the
-parity suite of the hot path red.  Drop the marker after the first green run."""
+The per-thread code of both kernels is also replayed on the host bit for bit by tests/test_preprocess_core_cpu.py; these tests
+ran green on a B200 in round 1 (7 passed as XPASS), so they are ordinary tests now: a mismatch fails the suite."""
 import hashlib
 import os
 
@@ -16,8 +14,7 @@ import torch
 import clip_preprocess_oracle as P
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first device run of the pre-processing kernels (host replay is bit-exact)")]
+pytestmark = pytest.mark.gpu
 
 
 def sha(a):

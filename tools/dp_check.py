@@ -23,13 +23,26 @@ g = torch.Generator().manual_seed(5)
 px = torch.randn(B, 3, cfg["v_image"], cfg["v_image"], generator=g)
 ids = torch.randint(3, cfg["t_vocab"] - 4, (B, 20), generator=g)
 ids[:, 0], ids[:, 1], ids[:, 2] = 1, cfg["t_vocab"] - 4, cfg["t_vocab"] - 3
-dp = generate_dp(m, ids, px, n_new)                     # every rank: its slice + per-step NCCL all-gather
+calls = {"n": 0}
+_orig = dist.all_gather_into_tensor
+
+
+def _counting(*a, **k):
+    calls["n"] += 1
+    return _orig(*a, **k)
+
+
+dist.all_gather_into_tensor = _counting
+dp = generate_dp(m, ids, px, n_new)                     # every rank: its slice; the NCCL all-gather runs inside the decode graphs
+dp2 = generate_dp(m, ids, px, n_new)                    # replay of the captured graphs
+tiny = generate_dp(m, ids[:1], px[:1], n_new)           # fewer requests than ranks: the other ranks only take part in the exchange
+in_graph = calls["n"] == 0 and m._engine.dp_width > 0   # no torch collective per token: the exchange belongs to the native context
 single = m.generate(input_ids=ids.cuda(), pixel_values=px.cuda(), do_sample=False, max_new_tokens=n_new, eos_token_id=None, pad_token_id=0)
-ok = torch.equal(dp, single)
+ok = torch.equal(dp, single) and torch.equal(dp2, single) and torch.equal(tiny, single[:1])
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"[dp_check] world={world} B={B}: DP == single-GPU on every rank: {bool(flag.item())}")
+    print(f"[dp_check] world={world} B={B}: DP == single-GPU on every rank: {bool(flag.item())}; in-graph exchange: {in_graph}")
     print(dp.tolist())
 dist.barrier()
 dist.destroy_process_group()
