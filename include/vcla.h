@@ -148,6 +148,37 @@ int vcla_decode_multi(vcla_ctx* ctx, int32_t* tok_inout_dev, int B, int n_steps,
  * (async on `stream`): lets a greedy loop run as pure graph replays with no per-step host or torch work. */
 int vcla_read_history(vcla_ctx* ctx, int32_t* dst_dev, int B, int n_steps, vcla_stream stream);
 
+/* ---- device-side sampling ---------------------------------------------------------------------
+ * chat()'s real default is sampling (models/visualcla/modeling_utils.py:36-47: temperature 0.5, top_k 40, top_p 0.9,
+ * repetition_penalty 1.1, no_repeat_ngram_size 15).  With a sampler set, vcla_prefill / vcla_decode_step / vcla_decode_multi
+ * replace the argmax by ONE fused kernel per step -- HF's processor chain in HF's order (RepetitionPenalty, NoRepeatNGram,
+ * min_new_tokens EOS mask, Temperature, TopK, TopP; HF:generation/logits_process.py) + a Philox-keyed multinomial draw -- on the
+ * device token history (with inputs_embeds HF's processors only see the new tokens), inside the captured CUDA graph: no logits
+ * leave the device, no host work per token.  do_sample = 0 takes the argmax of the processed scores (greedy + penalties).
+ * A sequence that emitted an EOS id keeps producing pad_token_id (sticky per-sequence flag, vcla_read_finished).
+ * The parameters live in device memory: changing them does not re-capture graphs. */
+typedef struct {
+  int do_sample;
+  float repetition_penalty;     /* 1 = off */
+  int no_repeat_ngram_size;     /* 0 = off */
+  float temperature;            /* 1 = off */
+  int top_k;                    /* 1..1024, required when do_sample */
+  float top_p;                  /* 1 = off */
+  int min_new_tokens;
+  int n_eos;                    /* <= 4 */
+  int eos_token_id[4];
+  int pad_token_id;
+  uint64_t seed;                /* draw = Philox4x32-10(key = seed, counter = (step, sequence)) */
+} vcla_sampler;
+int vcla_sampler_supported(const vcla_ctx* ctx);   /* 1 when the vocabulary row fits one CTA's shared memory */
+int vcla_set_sampler(vcla_ctx* ctx, const vcla_sampler* sampler_or_null, vcla_stream stream);   /* NULL: back to greedy argmax */
+int vcla_read_finished(vcla_ctx* ctx, int32_t* dst_dev, int B, vcla_stream stream);
+/* Operator-level entry (parity tests): the same kernel on caller logits (B,V) f32 and a token history [L][B] int32; writes the
+ * chosen tokens (B) and, if not NULL, the processed scores (B,V) (-inf = filtered) exactly as HF's chain would return them.
+ * Synchronises. */
+int vcla_op_sample(const float* logits_dev, int B, int V, const int32_t* history_dev, int L, const vcla_sampler* sampler,
+                   int32_t* tok_dev, float* scores_out_dev, vcla_stream stream);
+
 /* ---- data parallel over the GPUs of one box (the reference has no DP of its own) ----------------
  * Requests are independent through the whole path, so each rank (one process + one context per GPU) runs a contiguous slice of
  * the batch and the ONLY exchange is one NCCL all-gather of the chosen token ids per decode step.  After vcla_nccl_init the
@@ -195,7 +226,7 @@ int vcla_op_rmsnorm(const float* x, int rows, int D, const float* w, float eps, 
 int vcla_bench_decode_gemm(vcla_ctx* ctx, int which, int B, int reps, float* avg_us, int64_t* weight_bytes, vcla_stream stream);
 /* Timeline trace for profiles/: when enabled, CTA (0,0,0) of every kernel appends {tag, t_entry, t_dependency_resolved, t_exit}
  * (%globaltimer, ns).  Tags: 1 swap-AB GEMM, 2 GEMM, 3 prefill attention, 4 decode attention, 5 layernorm, 6 rmsnorm, 7 rope+cache,
- * 8 resid+rmsnorm, 9 silu*mul, 10/11 logits+argmax, 12 advance, 13 embed.  vcla_trace_read synchronises and clears. */
+ * 8 resid+rmsnorm, 9 silu*mul, 10/11 logits+argmax, 12 advance, 13 embed, 14 sampler.  vcla_trace_read synchronises and clears. */
 int vcla_trace_enable(vcla_ctx* ctx, int max_events);
 int vcla_trace_read(vcla_ctx* ctx, uint64_t* dst_host, int max_events, int* n_events);
 /* enable/disable programmatic dependent launch for subsequently enqueued kernels (process-wide) */

@@ -64,6 +64,7 @@ def test_decode_refuses_to_run_past_the_context_capacity():
     full = _gen(m, ids, px, 20)                            # exactly fills the context
     assert full.shape == (2, 20)
     tok = torch.zeros(2, dtype=torch.int32, device="cuda")
+    eng.decode_step(tok, tok, None)                        # feeding the 20th token fills the last slot (index 39)
     with pytest.raises(N.NativeError, match="capacity"):
         eng.decode_step(tok, tok, None)                    # one more step would index past the sequence's pages
     with pytest.raises(N.NativeError, match="capacity"):

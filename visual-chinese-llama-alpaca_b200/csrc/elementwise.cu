@@ -518,6 +518,13 @@ int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, in
   return 0;
 }
 
+int dec_logits_reduce(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, const float* rstd,
+                      float* cand_val, int32_t* cand_idx, cudaStream_t st) {
+  if (!logits || !cand_val || !cand_idx) { set_error("dec_logits_reduce: missing buffers"); return -1; }
+  VCLA_LAUNCH(dec_logits_stage1, dim3(kArgChunks, B), dim3(256), 0, st, partial, splits, ws_rows, ldp, V, logits, ld_logits, cand_val, (int*)cand_idx, rstd);
+  return 0;
+}
+
 // data parallel: append the all-gathered tokens of this step to the global history [step][world * width]
 __global__ void dp_unpack_kernel(const int32_t* __restrict__ recv, int n, int32_t* __restrict__ hist, int32_t* __restrict__ dp_step) {
   const int s = *dp_step;

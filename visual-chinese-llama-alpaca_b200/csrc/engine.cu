@@ -52,13 +52,14 @@ struct TextLayer {
 };
 
 struct GraphKey {
-  int B; const void* tok_in; const void* logits; const void* tok_out; int n_steps = 1; int dp = 0;
+  int B; const void* tok_in; const void* logits; const void* tok_out; int n_steps = 1; int dp = 0; int samp = 0;
   bool operator<(const GraphKey& o) const {
     if (B != o.B) return B < o.B;
     if (tok_in != o.tok_in) return tok_in < o.tok_in;
     if (logits != o.logits) return logits < o.logits;
     if (n_steps != o.n_steps) return n_steps < o.n_steps;
     if (dp != o.dp) return dp < o.dp;
+    if (samp != o.samp) return samp < o.samp;
     return tok_out < o.tok_out;
   }
 };
@@ -107,6 +108,8 @@ struct vcla_ctx {
   bool dp_on() const { return comm != nullptr && dp_active; }
   int32_t *dp_send = nullptr, *dp_recv = nullptr, *dp_hist = nullptr, *dp_step = nullptr;
   cudaStream_t dp_stream = nullptr; cudaEvent_t dp_fork = nullptr, dp_join = nullptr; bool dp_pending = false;
+  // device-side sampling (vcla_set_sampler): replaces the argmax by the fused logits-processor chain + draw
+  SamplerParams* samp_params = nullptr; float* samp_logits = nullptr; int32_t* finished = nullptr; bool samp_on = false;
   int64_t len_bound = 0;   // host-side upper bound of the cached tokens per sequence (prefill S + decode steps issued since)
   // vision activations
   bf16 *v_im2col = nullptr, *v_norm = nullptr, *v_qkv = nullptr, *v_attn = nullptr, *v_ffn = nullptr;
@@ -325,6 +328,9 @@ void layout_activations(vcla_ctx* c) {
   c->rope_sin = a_alloc<float>(c, (size_t)(g.max_seq + 1) * 64);
   c->cand_val = a_alloc<float>(c, Bp * kArgmaxChunks);
   c->cand_idx = a_alloc<int32_t>(c, Bp * kArgmaxChunks);
+  c->samp_params = a_alloc<SamplerParams>(c, 1);
+  c->samp_logits = a_alloc<float>(c, Bp * (size_t)g.t_vocab);
+  c->finished = a_alloc<int32_t>(c, Bp);
 }
 
 // Split-K factor of a decode GEMM (row tiles of 128 x `splits` work units on 2 persistent CTAs per SM).  Measured on B200
@@ -466,7 +472,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   cudaMemcpy(c->img_row_default, two.data(), two.size() * 4, cudaMemcpyHostToDevice);
   if (const char* e = getenv("VCLA_ATTN_PERSISTENT")) c->attn_persistent_mode = atoi(e);
   if (const char* e = getenv("VCLA_ATTN_PERSISTENT_GRID")) c->attn_persistent_grid = atoi(e);
-  if (rope_fill_tables(g.max_seq + 1, 128, g.rope_theta, c->rope_cos, c->rope_sin) || attention_init() || vcla_reset(c, nullptr)) { vcla_destroy(c); return -1; }
+  if (rope_fill_tables(g.max_seq + 1, 128, g.rope_theta, c->rope_cos, c->rope_sin) || attention_init() || sampler_init() || vcla_reset(c, nullptr)) { vcla_destroy(c); return -1; }
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("vcla_create: device error %s", cudaGetErrorString(cudaGetLastError())); vcla_destroy(c); return -1; }
   *out = c;
   return 0;
@@ -610,6 +616,7 @@ int vcla_reset(vcla_ctx* c, vcla_stream stream) {
   // every page back on the free stack, no sequence owns any
   if (kv_reset(c->kv_free, c->kv_order, c->kv_state, c->kv_npages, c->total_pages, c->cfg.max_batch, (cudaStream_t)stream)) return -1;
   if (c->dp_step) VCLA_CUDA_OK(cudaMemsetAsync(c->dp_step, 0, 4, (cudaStream_t)stream));
+  VCLA_CUDA_OK(cudaMemsetAsync(c->finished, 0, 64 * 4, (cudaStream_t)stream));
   c->len_bound = 0;
   return 0;
 }
@@ -749,6 +756,16 @@ static int dp_wait(vcla_ctx* c, cudaStream_t st) {
 static int logits_argmax(vcla_ctx* c, int B, float* logits, int32_t* tok, const float* rstd, int fork, cudaStream_t st) {
   const vcla_config& g = c->cfg;
   if (c->dp_on() && dp_wait(c, st)) return -1;            // the previous step's exchange must have read dp_send before it is rewritten
+  if (c->samp_on) {
+    // logits -> [repetition penalty, no-repeat-ngram, temperature, top-k, top-p, draw] in one kernel; raw logits stay available
+    float* lg = logits ? logits : c->samp_logits;
+    count(c, 2);
+    if (dec_logits_reduce(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, lg, g.t_vocab, rstd, c->cand_val, c->cand_idx, st)) return -1;
+    if (dec_sample(lg, g.t_vocab, g.t_vocab, B, c->tok_hist, c->step_idx, c->samp_params, tok, c->tok_hist, c->dp_on() ? c->dp_send : nullptr, c->finished,
+                   nullptr, st)) return -1;
+    if (c->dp_on()) return dp_gather(c, st, fork);
+    return 0;
+  }
   count(c, 2);
   if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok, c->tok_hist, c->step_idx, rstd, c->cand_val, c->cand_idx,
                         c->dp_on() ? c->dp_send : nullptr, st)) return -1;
@@ -885,7 +902,7 @@ static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logi
 }
 
 static int decode_graph(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, int n_steps, cudaStream_t st) {
-  GraphKey key{B, tok_in, logits, tok_out, n_steps, c->dp_on() ? 1 : 0};
+  GraphKey key{B, tok_in, logits, tok_out, n_steps, c->dp_on() ? 1 : 0, c->samp_on ? 1 : 0};
   auto it = c->graphs.find(key);
   if (it == c->graphs.end()) {
     const int64_t before = c->launches;
@@ -959,6 +976,63 @@ int vcla_decode_multi(vcla_ctx* c, int32_t* tok_inout, int B, int n_steps, vcla_
   if (decode_capacity(c, n_steps)) return -1;
   const int rc = decode_graph(c, tok_inout, B, nullptr, tok_inout, n_steps, (cudaStream_t)stream);
   if (rc == 0) c->len_bound += n_steps;
+  return rc;
+}
+
+// -------------------------------------------------------------------------------------------------
+// device-side sampling
+// -------------------------------------------------------------------------------------------------
+static int sampler_to_params(const vcla_sampler* s, SamplerParams* p) {
+  if (s->n_eos < 0 || s->n_eos > 4) { set_error("sampler: at most 4 eos ids"); return -1; }
+  if (s->do_sample && (s->top_k < 1 || s->top_k > 1024)) { set_error("sampler: the device path needs 1 <= top_k <= 1024 (got %d)", s->top_k); return -1; }
+  if (s->do_sample && !(s->temperature > 0.f)) { set_error("sampler: temperature must be > 0"); return -1; }
+  if (!(s->repetition_penalty > 0.f)) { set_error("sampler: repetition_penalty must be > 0"); return -1; }
+  if (s->top_p <= 0.f || s->top_p > 1.f) { set_error("sampler: top_p must be in (0, 1]"); return -1; }
+  memset(p, 0, sizeof(*p));
+  p->do_sample = s->do_sample ? 1 : 0;
+  p->rep_penalty = s->repetition_penalty; p->no_repeat_ngram = s->no_repeat_ngram_size > 0 ? s->no_repeat_ngram_size : 0;
+  p->temperature = s->temperature; p->top_k = s->top_k; p->top_p = s->top_p;
+  p->one_minus_top_p = (float)(1.0 - (double)s->top_p);
+  p->min_new_tokens = s->min_new_tokens; p->n_eos = s->n_eos; p->pad_id = s->pad_token_id;
+  for (int i = 0; i < s->n_eos; ++i) p->eos[i] = s->eos_token_id[i];
+  p->seed = s->seed;
+  return 0;
+}
+
+int vcla_sampler_supported(const vcla_ctx* c) { return c ? sampler_supported(c->cfg.t_vocab) : 0; }
+
+int vcla_set_sampler(vcla_ctx* c, const vcla_sampler* s, vcla_stream stream) {
+  if (!c) return -1;
+  if (s == nullptr) { c->samp_on = false; return 0; }
+  if (!sampler_supported(c->cfg.t_vocab)) { set_error("sampler: vocabulary %d does not fit the device sampler", c->cfg.t_vocab); return -1; }
+  SamplerParams p;
+  if (sampler_to_params(s, &p)) return -1;
+  // pageable source: the driver stages it before returning, so `p` may go out of scope
+  VCLA_CUDA_OK(cudaMemcpyAsync(c->samp_params, &p, sizeof(p), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  c->samp_on = true;
+  return 0;
+}
+
+int vcla_read_finished(vcla_ctx* c, int32_t* dst_dev, int B, vcla_stream stream) {
+  if (!c || !dst_dev || B < 1 || B > 64) { set_error("vcla_read_finished: bad arguments"); return -1; }
+  VCLA_CUDA_OK(cudaMemcpyAsync(dst_dev, c->finished, (size_t)B * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int vcla_op_sample(const float* logits_dev, int B, int V, const int32_t* history_dev, int L, const vcla_sampler* s, int32_t* tok_dev,
+                   float* scores_out_dev, vcla_stream stream) {
+  if (!logits_dev || !s || B < 1 || V < 1 || L < 0 || (L > 0 && !history_dev)) { set_error("vcla_op_sample: bad arguments"); return -1; }
+  SamplerParams p;
+  if (sampler_to_params(s, &p) || sampler_init()) return -1;
+  uint8_t* scratch = nullptr;
+  VCLA_CUDA_OK(cudaMalloc(&scratch, sizeof(SamplerParams) + 16));
+  cudaStream_t st = (cudaStream_t)stream;
+  VCLA_CUDA_OK(cudaMemcpyAsync(scratch, &p, sizeof(p), cudaMemcpyHostToDevice, st));
+  VCLA_CUDA_OK(cudaMemcpyAsync(scratch + sizeof(SamplerParams), &L, 4, cudaMemcpyHostToDevice, st));
+  const int rc = dec_sample(logits_dev, V, V, B, history_dev, (const int32_t*)(scratch + sizeof(SamplerParams)), (const SamplerParams*)scratch, tok_dev, nullptr,
+                            nullptr, nullptr, scores_out_dev, st);
+  cudaStreamSynchronize(st);
+  cudaFree(scratch);
   return rc;
 }
 

@@ -163,6 +163,27 @@ constexpr int kArgmaxChunks = 32;
 int dec_logits_argmax(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits,
                       int32_t* tok, int32_t* history, const int32_t* step_idx, const float* rstd, float* cand_val,
                       int32_t* cand_idx, int32_t* dp_send, cudaStream_t st);
+// stage 1 only: logits[b, :] = rstd[b] * sum_s partial (the sampler consumes them)
+int dec_logits_reduce(const float* partial, int splits, int ws_rows, int ldp, int B, int V, float* logits, int ld_logits, const float* rstd,
+                      float* cand_val, int32_t* cand_idx, cudaStream_t st);
+// ---- device-side sampling (sampler.cu) ----------------------------------------------------------------------------------
+struct SamplerParams {     // lives in device memory: graphs captured once serve every parameter set
+  int do_sample;           // 0: argmax of the processed scores
+  float rep_penalty;       // 1 = off
+  int no_repeat_ngram;     // 0 = off
+  float temperature;       // 1 = off
+  int top_k;               // 1..1024 (required when do_sample)
+  float top_p;             // 1 = off
+  float one_minus_top_p;   // (float)(1.0 - (double)top_p): the constant HF compares the cumulative probabilities with
+  int min_new_tokens, n_eos, pad_id;
+  int eos[4];
+  unsigned long long seed;
+};
+int sampler_supported(int V);
+int sampler_init();
+// history: [L][B] int32 with L = *step_idx; writes tok[b], history_out[L][b], dp_send[b]; finished[b] (nullable): sticky EOS flag
+int dec_sample(const float* logits, int ld, int V, int B, const int32_t* history, const int32_t* step_idx, const SamplerParams* params_dev,
+               int32_t* tok, int32_t* history_out, int32_t* dp_send, int32_t* finished, float* scores_out, cudaStream_t st);
 int dp_unpack(const int32_t* recv, int n, int32_t* hist, int32_t* dp_step, cudaStream_t st);
 // decode step entry: resid[b,:] = table[ids[b]] ; xw = bf16(resid * norm_w) ; rstd[b] = rsqrt(mean(resid^2) + eps)
 int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps,

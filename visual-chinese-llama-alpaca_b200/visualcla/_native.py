@@ -22,6 +22,12 @@ class VclaConfig(C.Structure):
     ]
 
 
+class VclaSampler(C.Structure):
+    _fields_ = [("do_sample", C.c_int), ("repetition_penalty", C.c_float), ("no_repeat_ngram_size", C.c_int), ("temperature", C.c_float),
+                ("top_k", C.c_int), ("top_p", C.c_float), ("min_new_tokens", C.c_int), ("n_eos", C.c_int), ("eos_token_id", C.c_int * 4),
+                ("pad_token_id", C.c_int), ("seed", C.c_uint64)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -51,6 +57,10 @@ _SIGNATURES = [
     ("vcla_decode_step", C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P]),
     ("vcla_decode_multi", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     ("vcla_read_history", C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    ("vcla_sampler_supported", C.c_int, [_P]),
+    ("vcla_set_sampler", C.c_int, [_P, C.POINTER(VclaSampler), _P]),
+    ("vcla_read_finished", C.c_int, [_P, _P, C.c_int, _P]),
+    ("vcla_op_sample", C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.POINTER(VclaSampler), _P, _P, _P]),
     ("vcla_nccl_unique_id", C.c_int, [_P]),
     ("vcla_nccl_init", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     ("vcla_allgather_tokens", C.c_int, [_P, _P, C.c_int, _P, _P]),

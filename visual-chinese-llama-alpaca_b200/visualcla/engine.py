@@ -229,6 +229,41 @@ class Engine:
             N.check(self.lib.vcla_read_history_dp(self._ctx, N.ptr(out), n_steps, self._stream()), "vcla_read_history_dp")
         return out
 
+    # ---- device-side sampling (include/vcla.h, "device-side sampling") -------------------------------------
+    def sampler_supported(self) -> bool:
+        return bool(self.lib.vcla_sampler_supported(self._ctx))
+
+    @staticmethod
+    def sampler_spec(do_sample=False, repetition_penalty=1.0, no_repeat_ngram_size=0, temperature=1.0, top_k=0, top_p=1.0,
+                     min_new_tokens=0, eos_token_id=(), pad_token_id=0, seed=0) -> "N.VclaSampler":
+        eos = list(eos_token_id)
+        arr = (C.c_int * 4)(*(eos + [0] * (4 - len(eos)))[:4])
+        return N.VclaSampler(1 if do_sample else 0, float(repetition_penalty), int(no_repeat_ngram_size or 0), float(temperature), int(top_k or 0),
+                             float(top_p), int(min_new_tokens or 0), len(eos), arr, int(pad_token_id), int(seed) & (2 ** 64 - 1))
+
+    def set_sampler(self, spec: Optional["N.VclaSampler"]):
+        """spec = sampler_spec(...): prefill / decode pick tokens with the fused device sampler; None: back to argmax."""
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_set_sampler(self._ctx, C.byref(spec) if spec is not None else None, self._stream()), "vcla_set_sampler")
+
+    def read_finished(self, B: int) -> torch.Tensor:
+        out = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_read_finished(self._ctx, N.ptr(out), B, self._stream()), "vcla_read_finished")
+        return out
+
+    def op_sample(self, logits: torch.Tensor, history: Optional[torch.Tensor], spec: "N.VclaSampler", return_scores: bool = True):
+        """The sampler kernel on caller data: logits (B,V) f32, history (B,L) tokens.  -> (tokens (B,) int32, processed scores (B,V))."""
+        lg = logits.to(self.device, torch.float32).contiguous()
+        B, V = lg.shape
+        L = 0 if history is None else history.shape[1]
+        hist = None if L == 0 else history.to(self.device, torch.int32).t().contiguous()     # kernel layout: [L][B]
+        tok = torch.empty(B, dtype=torch.int32, device=self.device)
+        scores = torch.empty(B, V, dtype=torch.float32, device=self.device) if return_scores else None
+        with torch.cuda.device(self.device):
+            N.check(self.lib.vcla_op_sample(N.ptr(lg), B, V, N.ptr(hist), L, C.byref(spec), N.ptr(tok), N.ptr(scores), self._stream()), "vcla_op_sample")
+        return tok, scores
+
     def read_history(self, B: int, n_steps: int) -> torch.Tensor:
         """(n_steps, B) int32 CUDA tensor: tokens chosen by the prefill (row 0) and each decode step since."""
         out = torch.empty(n_steps, B, dtype=torch.int32, device=self.device)

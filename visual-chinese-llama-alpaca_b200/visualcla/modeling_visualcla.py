@@ -376,7 +376,7 @@ class VisualCLAModel:
         gc = copy.deepcopy(generation_config) if generation_config is not None else GenerationConfig()
         unused = gc.update(**kwargs)
         for k in list(unused):
-            if k in ("output_scores", "output_logits", "return_dict_in_generate", "use_cache"):
+            if k in ("output_scores", "output_logits", "return_dict_in_generate", "use_cache", "tfs", "top_a", "mirostat_mode", "mirostat_tau", "mirostat_eta"):
                 setattr(gc, k, unused.pop(k))
         if unused:
             raise ValueError(f"generate(): unsupported arguments {sorted(unused)}")
@@ -440,6 +440,9 @@ class VisualCLAModel:
         out = torch.full((B, max_new), pad, dtype=torch.int64, device=dev)
         all_logits: List[torch.Tensor] = []
 
+        spec = self._device_sampler_spec(gc, eos, pad, min_new, logits_processor, crit, processors)
+        if spec is not None:
+            return self._generate_on_device(spec, input_ids, mode, rows, pads, B, max_new, eos, pad, gc, tok)
         last, first_tok, _ = eng.prefill(input_ids, mode, rows, all_logits=False, last_logits=need_logits, left_pad=pads, pos_from_mask=True)
         if not need_logits and not eos and not crit:
             # pure greedy, fixed length: graph replays only; tokens come from the device-side history the graph appends to
@@ -514,6 +517,71 @@ class VisualCLAModel:
             return SimpleNamespace(sequences=result, logits=tuple(all_logits) if all_logits else None, scores=None)
         return result
 
+    # ---- sampling / EOS on the device: one fused kernel per step inside the decode graph ---------------------
+    def _device_sampler_spec(self, gc, eos, pad, min_new, extra_processors, crit, processors):
+        """-> a native sampler spec when this call can run entirely on the device, else None (host logits-processor path).
+        On the device: greedy or sampling with repetition_penalty / no_repeat_ngram_size / temperature / top_k (1..1024) / top_p and
+        up to 4 EOS ids -- the reference's DEFAULT_GENERATION_CONFIG (ref modeling_utils.py:36-47) is such a call.  Anything else
+        (custom processors, stopping criteria / streaming, TFS / Top-A / Mirostat, top_k disabled, logits or scores requested)
+        keeps the per-step host path."""
+        eng = self._engine
+        if os.environ.get("VCLA_HOST_SAMPLER") == "1" or not hasattr(eng, "sampler_supported") or not eng.sampler_supported():
+            return None
+        if extra_processors or crit or getattr(gc, "output_logits", False) or getattr(gc, "output_scores", False) or len(eos) > 4:
+            return None
+        sampling = bool(gc.do_sample)
+        rp = getattr(gc, "repetition_penalty", None) or 1.0
+        ng = getattr(gc, "no_repeat_ngram_size", None) or 0
+        if not sampling and rp == 1.0 and ng == 0 and not eos:
+            return None                                   # plain fixed-length greedy: the argmax graphs
+        if getattr(gc, "mirostat_mode", 0) == 2:
+            return None
+        for name, on in (("tfs", lambda v: 0.0 <= v < 1.0), ("top_a", lambda v: 0.0 < v <= 1.0), ("typical_p", lambda v: v < 1.0),
+                         ("min_p", lambda v: v > 0.0), ("epsilon_cutoff", lambda v: v > 0.0), ("eta_cutoff", lambda v: v > 0.0)):
+            v = getattr(gc, name, None)
+            if v is not None and on(v):
+                return None
+        temperature = gc.temperature if (sampling and gc.temperature is not None) else 1.0
+        top_k = gc.top_k if sampling else 0
+        top_p = gc.top_p if (sampling and gc.top_p is not None) else 1.0
+        if sampling and (top_k is None or not 1 <= top_k <= 1024 or temperature <= 0 or not 0.0 < top_p <= 1.0):
+            return None
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # from torch's global generator: torch.manual_seed reproduces a run
+        return eng.sampler_spec(do_sample=sampling, repetition_penalty=rp, no_repeat_ngram_size=ng, temperature=temperature, top_k=top_k or 0,
+                                top_p=top_p, min_new_tokens=min_new, eos_token_id=eos, pad_token_id=pad, seed=seed)
+
+    def _generate_on_device(self, spec, input_ids, mode, rows, pads, B, max_new, eos, pad, gc, tok):
+        eng = self._engine
+        eng.set_sampler(spec)
+        try:
+            _, first_tok, _ = eng.prefill(input_ids, mode, rows, all_logits=False, last_logits=False, left_pad=pads, pos_from_mask=True)
+            tok.copy_(first_tok)
+            n_done = 1
+            if not eos:
+                eng.decode_many(tok, max_new - 1)
+                n_done = max_new
+            else:
+                # EOS: graphs of 8 steps, one host poll of the per-sequence finished flags between them (sequences are independent
+                # and a finished one only emits pad, so running a few steps past the last EOS cannot change a retained token)
+                while n_done < max_new:
+                    if bool(eng.read_finished(B).bool().all()):
+                        break
+                    k = min(8, max_new - n_done)
+                    eng.decode_many(tok, k)
+                    n_done += k
+            result = eng.read_history(B, n_done).t().to(torch.int64)
+        finally:
+            eng.set_sampler(None)
+        if eos:
+            hit = torch.zeros_like(result, dtype=torch.bool)
+            for e in eos:
+                hit |= result == e
+            first = torch.where(hit.any(1), hit.float().argmax(1) + 1, torch.full((B,), n_done, device=result.device))
+            result = result[:, : int(first.max())]        # cut where the last sequence finished (HF's per-step check)
+        if getattr(gc, "return_dict_in_generate", False):
+            return SimpleNamespace(sequences=result, logits=None, scores=None)
+        return result
+
     @staticmethod
     def _build_processors(gc, extra):
         """HF logits processors for the sampling knobs of DEFAULT_GENERATION_CONFIG
@@ -535,9 +603,21 @@ class VisualCLAModel:
                 procs.append(lp.TopKLogitsWarper(top_k=gc.top_k, min_tokens_to_keep=1))
             if gc.top_p is not None and gc.top_p < 1.0:
                 procs.append(lp.TopPLogitsWarper(top_p=gc.top_p, min_tokens_to_keep=1))
+            from . import modeling_utils as mu
+            if getattr(gc, "mirostat_mode", 0) == 2:
+                # ref modeling_utils.py:366-371: Mirostat v2 joins the warpers and "disables samplers other than temperature" with a
+                # remove-while-iterating loop -- which skips the element after every removal (temperature, top-k, top-p -> top-p
+                # survives).  Replayed literally so the same generation config samples from the same distribution.
+                n_fixed = len(procs) - sum(isinstance(p, (lp.TemperatureLogitsWarper, lp.TopKLogitsWarper, lp.TopPLogitsWarper)) for p in procs)
+                warpers = procs[n_fixed:]
+                for w in warpers:
+                    if not isinstance(w, lp.TemperatureLogitsWarper):
+                        warpers.remove(w)
+                procs = procs[:n_fixed] + warpers
+                procs.append(mu.MirostatLogitsWarper(mirostat_mode=2, mirostat_tau=getattr(gc, "mirostat_tau", 5), mirostat_eta=getattr(gc, "mirostat_eta", 0.1)))
+                return procs
             for name, kw in (("tfs", "tfs"), ("top_a", "top_a")):
                 val = getattr(gc, name, None)
                 if val is not None and ((name == "tfs" and 0.0 <= val < 1.0) or (name == "top_a" and 0.0 < val <= 1.0)):
-                    from . import modeling_utils as mu
                     procs.append(mu.TailFreeLogitsWarper(tfs=val) if name == "tfs" else mu.TopALogitsWarper(top_a=val))
         return procs
