@@ -113,6 +113,31 @@ int rmsnorm(const float* x, int rows, int D, const float* w, float eps, bf16* y,
   return 0;
 }
 
+__global__ void prenorm_rows_kernel(const float* __restrict__ x, int D, const float* __restrict__ w, bf16* __restrict__ xw, float* __restrict__ ssq, int slots) {
+  __shared__ float red[32];
+  TraceScope trace(6);
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.dep();
+  const size_t row = blockIdx.x;
+  const float* xr = x + row * D;
+  float q = 0.f;
+  for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    const float4 wv = *reinterpret_cast<const float4*>(w + i);
+    q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    *reinterpret_cast<uint2*>(xw + row * D + i) = make_uint2(pack_bf16x2(v.x * wv.x, v.y * wv.y), pack_bf16x2(v.z * wv.z, v.w * wv.w));
+  }
+  q = block_sum(q, red);
+  for (int sidx = threadIdx.x; sidx < slots; sidx += blockDim.x) ssq[row * slots + sidx] = sidx == 0 ? q : 0.f;
+}
+int prenorm_rows(const float* x, int rows, int D, const float* w, bf16* xw, float* ssq, int slots, cudaStream_t st) {
+  if (D % 4) { set_error("prenorm_rows: D %% 4 != 0"); return -1; }
+  if (rows == 0) return 0;
+  VCLA_LAUNCH(prenorm_rows_kernel, dim3(rows), dim3(D >= 2048 ? 256 : 128), 0, st, x, D, w, xw, ssq, slots);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // ViT front end
 // ------------------------------------------------------------------------------------------------
@@ -222,7 +247,7 @@ int embed_tokens_i32(const int32_t* ids, int B, int D, const bf16* table, int vo
 // decode step entry (one CTA per sequence): embedding row -> fp32 residual, bf16 GEMM operand pre-multiplied by the first
 // layer's RMSNorm weight, and the row's deferred scale 1/rms
 __global__ void dec_embed_kernel(const int32_t* __restrict__ ids, int D, const bf16* __restrict__ table, int vocab, float* __restrict__ resid,
-                                 const float* __restrict__ norm_w, float eps, bf16* __restrict__ xw, float* __restrict__ rstd) {
+                                 const float* __restrict__ norm_w, float eps, bf16* __restrict__ xw, float* __restrict__ rstd, float* __restrict__ ssq, int slots) {
   __shared__ float red[32];
   TraceScope trace(13);
   pdl_launch_dependents();   // dependents may become resident early; they block in their own griddepcontrol.wait
@@ -248,11 +273,14 @@ __global__ void dec_embed_kernel(const int32_t* __restrict__ ids, int D, const b
     for (int j = 0; j < 8; ++j) q += f[j] * f[j];
   }
   q = block_sum(q, red);
-  if (threadIdx.x == 0) rstd[b] = rsqrtf(q / D + eps);
+  if (threadIdx.x == 0 && rstd != nullptr) rstd[b] = rsqrtf(q / D + eps);
+  // deferred-norm chain head: the row's sum of squares in slot 0, the other slots empty
+  if (ssq != nullptr) for (int i = threadIdx.x; i < slots; i += blockDim.x) ssq[(size_t)b * slots + i] = i == 0 ? q : 0.f;
 }
-int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps, bf16* xw, float* rstd, cudaStream_t st) {
+int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps, bf16* xw, float* rstd,
+              float* ssq, int slots, cudaStream_t st) {
   if (D % 8) { set_error("dec_embed: D %% 8 != 0"); return -1; }
-  VCLA_LAUNCH(dec_embed_kernel, dim3(B), dim3(256), 0, st, ids, D, table, vocab, resid, norm_w, eps, xw, rstd);
+  VCLA_LAUNCH(dec_embed_kernel, dim3(B), dim3(256), 0, st, ids, D, table, vocab, resid, norm_w, eps, xw, rstd, ssq, slots);
   return 0;
 }
 

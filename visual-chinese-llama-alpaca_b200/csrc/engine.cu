@@ -118,6 +118,8 @@ struct vcla_ctx {
   bf16 *r_hidden_bf16 = nullptr, *r_qkv = nullptr, *r_kvimg = nullptr, *r_ctx = nullptr, *r_ffn = nullptr;
   // prefill activations
   float* resid = nullptr; bf16 *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hmid = nullptr;
+  float* p_ssq = nullptr;    // [max_prefill_tokens][t_hidden / 64] row statistics of the deferred-RMSNorm prefill schedule
+  int prefill_fused = 1;     // VCLA_PREFILL_FUSED=0: the 8-kernel/layer schedule with separate rmsnorm / rope_and_cache kernels
   // decode activations
   float* d_resid = nullptr; bf16 *d_xn = nullptr, *d_attn = nullptr, *d_h = nullptr;
   float *ws_qkv = nullptr, *ws_o = nullptr, *ws_gu = nullptr, *ws_d = nullptr, *ws_lm = nullptr;
@@ -125,6 +127,11 @@ struct vcla_ctx {
   int32_t* d_tok = nullptr;
   int32_t *tok_hist = nullptr, *step_idx = nullptr;
   float *d_rstd = nullptr, *d_ssq = nullptr; int32_t *cnt_o = nullptr, *cnt_gu = nullptr, *cnt_d = nullptr;   // fused split-K consumers (decode)
+  // decode schedule: 2 (default, batch <= 32) = cluster split-K GEMMs with fused consumers, 5 kernels / layer (gemm_decode.cu);
+  // 0 = split-K partials in an L2 workspace + separate consumer kernels, 8 kernels / layer; 1 = VCLA_FUSED_DECODE (below).
+  int decode_schedule = 2;
+  int csk_qkv = 0, csk_o = 0, csk_gu = 0, csk_d = 0, csk_lm = 0;   // CTAs per cluster (= K splits), chosen per batch on first use
+  int csk_batch = 0;
   int fused_decode = 0;   // VCLA_FUSED_DECODE=1: 5-kernel/layer schedule with in-GEMM split-K fixup. Correct (parity-tested) but measured slower
                           // on B200 (3.96 vs 3.32 ms/token at B=8): the fence->atomic->reload chain per tile outlasts a kernel boundary.   // tokens of every step since the last prefill, appended by the argmax kernel
   int sp_qkv = 1, sp_o = 1, sp_gu = 1, sp_d = 1, sp_lm = 1, kv_splits = 1;
@@ -297,6 +304,7 @@ void layout_activations(vcla_ctx* c) {
   c->qkv = a_alloc<bf16>(c, Tk * 3 * T);
   c->attn = a_alloc<bf16>(c, Tk * T);
   c->hmid = a_alloc<bf16>(c, Tk * F);
+  c->p_ssq = a_alloc<float>(c, Tk * ((T + 63) / 64));
   const size_t Bp = 64;  // decode operand rows (batch is processed in chunks of <= 64)
   c->d_resid = a_alloc<float>(c, Bp * T);
   c->d_xn = a_alloc<bf16>(c, Bp * T);
@@ -443,6 +451,10 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   c->sp_lm = pick_splits(g.t_vocab, g.t_hidden);
   if (const char* e = getenv("VCLA_L2_PREFETCH_KB")) c->l2_prefetch_kb = atoi(e);
   if (const char* e = getenv("VCLA_FUSED_DECODE")) c->fused_decode = atoi(e);
+  if (const char* e = getenv("VCLA_PREFILL_FUSED")) c->prefill_fused = atoi(e);
+  if (const char* e = getenv("VCLA_DECODE_SCHEDULE")) c->decode_schedule = !strcmp(e, "unfused") ? 0 : (!strcmp(e, "fix") ? 1 : 2);
+  if (c->fused_decode) c->decode_schedule = 1;
+  c->fused_decode = c->decode_schedule == 1;
   c->kv_splits = g.max_seq >= 1536 ? 4 : (g.max_seq >= 768 ? 2 : 1);   // context-driven minimum; raised per call for small batches
 
   if (gemm_init()) { delete c; return -1; }
@@ -753,21 +765,22 @@ static int dp_wait(vcla_ctx* c, cudaStream_t st) {
 }
 
 // logits reduce + argmax (+ token exchange when data parallel)
-static int logits_argmax(vcla_ctx* c, int B, float* logits, int32_t* tok, const float* rstd, int fork, cudaStream_t st) {
+static int logits_argmax(vcla_ctx* c, int B, float* logits, int32_t* tok, const float* rstd, int fork, cudaStream_t st, int lm_splits = 0) {
   const vcla_config& g = c->cfg;
+  const int sp_lm = lm_splits > 0 ? lm_splits : c->sp_lm;     // 1: ws_lm already holds the reduced logits (cluster split-K lm_head)
   if (c->dp_on() && dp_wait(c, st)) return -1;            // the previous step's exchange must have read dp_send before it is rewritten
   if (c->samp_on) {
     // logits -> [repetition penalty, no-repeat-ngram, temperature, top-k, top-p, draw] in one kernel; raw logits stay available
     float* lg = logits ? logits : c->samp_logits;
     count(c, 2);
-    if (dec_logits_reduce(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, lg, g.t_vocab, rstd, c->cand_val, c->cand_idx, st)) return -1;
+    if (dec_logits_reduce(c->ws_lm, sp_lm, B, g.t_vocab, B, g.t_vocab, lg, g.t_vocab, rstd, c->cand_val, c->cand_idx, st)) return -1;
     if (dec_sample(lg, g.t_vocab, g.t_vocab, B, c->tok_hist, c->step_idx, c->samp_params, tok, c->tok_hist, c->dp_on() ? c->dp_send : nullptr, c->finished,
                    nullptr, st)) return -1;
     if (c->dp_on()) return dp_gather(c, st, fork);
     return 0;
   }
   count(c, 2);
-  if (dec_logits_argmax(c->ws_lm, c->sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok, c->tok_hist, c->step_idx, rstd, c->cand_val, c->cand_idx,
+  if (dec_logits_argmax(c->ws_lm, sp_lm, B, g.t_vocab, B, g.t_vocab, logits, g.t_vocab, tok, c->tok_hist, c->step_idx, rstd, c->cand_val, c->cand_idx,
                         c->dp_on() ? c->dp_send : nullptr, st)) return -1;
   if (c->dp_on()) return dp_gather(c, st, fork);
   return 0;
@@ -802,6 +815,42 @@ int vcla_prefill(vcla_ctx* c, const int64_t* ids, int B, int T, int image_mode, 
     count(c); if (scatter_image_rows(c->img_embeds, B, nq, TH, rs, S, c->resid, st)) return -1;
   }
   const float scale = 1.0f / sqrtf(128.f);
+  if (c->prefill_fused) {
+    // 5 kernels per layer: RMSNorm is deferred (operand = bf16(resid * norm_w); the row scale commutes with the GEMM and is applied in
+    // the consuming GEMM's epilogue from the per-tile sums of squares the producing GEMM wrote), RoPE + KV-cache append run in the
+    // QKV GEMM's epilogue on the fp32 accumulator, SwiGLU in the gate/up epilogue, the residual add in the O / down epilogues.
+    const int slots = (TH + gemm_pick_bn(rows, TH) - 1) / gemm_pick_bn(rows, TH);
+    GemmRowScale rsc; rsc.ssq = c->p_ssq; rsc.slots = slots; rsc.inv_dim = 1.0f / (float)TH; rsc.eps = g.t_eps;
+    count(c); if (prenorm_rows(c->resid, rows, TH, c->tl[0].ln1, c->xn, c->p_ssq, slots, st)) return -1;
+    for (int i = 0; i < g.t_layers; ++i) {
+      const TextLayer& L = c->tl[i];
+      {
+        GemmCall gc; gc.A = c->xn; gc.B = L.wqkv; gc.M = rows; gc.N = 3 * TH; gc.K = TH; gc.lda = TH; gc.ldb = TH; gc.mode = GEMM_STORE_BF16; gc.out = c->qkv; gc.ldo = 3 * TH;
+        gc.rowscale = rsc;
+        gc.rope.cos = c->rope_cos; gc.rope.sin = c->rope_sin; gc.rope.kv_pages = L.kv; gc.rope.page_table = c->page_table; gc.rope.pages_per_seq = c->pages_per_seq;
+        gc.rope.page_tokens = c->page_tokens; gc.rope.S = S; gc.rope.T = TH; gc.rope.H = H; gc.rope.left_pad = left_pad; gc.rope.pos_from_mask = pos_from_mask;
+        count(c); if (gemm_tc(gc, st)) return -1;
+      }
+      AttnCall a; a.q = c->qkv; a.q_stride = 3 * TH; a.k0 = c->qkv + TH; a.v0 = c->qkv + 2 * TH; a.kv0_stride = 3 * TH; a.n0 = S;
+      a.out = c->attn; a.o_stride = TH; a.B = B; a.H = H; a.Sq = S; a.HD = 128; a.scale = scale; a.causal = 1; a.kv_start = left_pad;
+      count(c); if (attention_prefill(a, st)) return -1;
+      {
+        GemmCall gc; gc.A = c->attn; gc.B = L.wo; gc.M = rows; gc.N = TH; gc.K = TH; gc.lda = TH; gc.ldb = TH; gc.mode = GEMM_ADD_F32; gc.accumulate = 1; gc.out = c->resid; gc.ldo = TH;
+        gc.emit.norm_w = L.ln2; gc.emit.xw = c->xn; gc.emit.ldxw = TH; gc.emit.ssq_out = c->p_ssq;
+        count(c); if (gemm_tc(gc, st)) return -1;
+      }
+      {
+        GemmCall gc; gc.A = c->xn; gc.B = L.wgu; gc.M = rows; gc.N = 2 * F; gc.K = TH; gc.lda = TH; gc.ldb = TH; gc.mode = GEMM_SWIGLU_BF16; gc.out = c->hmid; gc.ldo = F;
+        gc.rowscale = rsc;
+        count(c); if (gemm_tc(gc, st)) return -1;
+      }
+      {
+        GemmCall gc; gc.A = c->hmid; gc.B = L.wd; gc.M = rows; gc.N = TH; gc.K = F; gc.lda = F; gc.ldb = F; gc.mode = GEMM_ADD_F32; gc.accumulate = 1; gc.out = c->resid; gc.ldo = TH;
+        gc.emit.norm_w = (i + 1 < g.t_layers) ? c->tl[i + 1].ln1 : c->final_norm; gc.emit.xw = c->xn; gc.emit.ldxw = TH; gc.emit.ssq_out = c->p_ssq;
+        count(c); if (gemm_tc(gc, st)) return -1;
+      }
+    }
+  } else
   for (int i = 0; i < g.t_layers; ++i) {
     const TextLayer& L = c->tl[i];
     count(c); if (rmsnorm(c->resid, rows, TH, L.ln1, g.t_eps, c->xn, st)) return -1;
@@ -866,14 +915,86 @@ static int decode_enqueue_unfused(vcla_ctx* c, const int32_t* tok_in, int B, flo
   return 0;
 }
 
+// ---- cluster split-K schedule (default for batch <= 32): 5 kernels per layer, no split-K workspace, no consumer kernels ----------
+// CTAs per cluster for a [M, K] weight at batch B: the choice that keeps the largest share of the 2 x SMs CTA slots busy over whole
+// rounds of cluster-tiles (clusters are gang-scheduled: floor(slots / S) of them are resident).
+static int csk_pick(int M, int K, int B) {
+  const int tiles = (M + 127) / 128, kb = (K + 63) / 64, bn = B <= 16 ? 16 : 32;
+  int best = 1; double best_score = -1.0;
+  for (int S = 1; S <= 8; ++S) {
+    const int per = (kb + S - 1) / S;
+    if ((kb + per - 1) / per != S) continue;                 // every K slice non-empty
+    if (S > 1 && kb / S < 2) break;
+    if (((B + S - 1) / S) * S > bn + 4) continue;            // reduce buffer columns
+    int ncl = gemm_csk_clusters(B, S);
+    if (ncl <= 0) continue;
+    if (ncl > tiles) ncl = tiles;
+    const int rounds = (tiles + ncl - 1) / ncl;
+    double score = (double)tiles * S / ((double)rounds * 2.0 * num_sms());
+    if (rounds >= 2) score += 0.02;                          // a second tile per CTA overlaps its loads with the first one's epilogue
+    if (score > best_score) { best_score = score; best = S; }
+  }
+  return best;
+}
+static int csk_prepare(vcla_ctx* c, int B) {
+  if (c->csk_batch == B) return 0;
+  const vcla_config& g = c->cfg;
+  int v[5] = {csk_pick(3 * g.t_hidden, g.t_hidden, B), csk_pick(g.t_hidden, g.t_hidden, B), csk_pick(2 * g.t_ffn, g.t_hidden, B),
+              csk_pick(g.t_hidden, g.t_ffn, B), csk_pick(g.t_vocab, g.t_hidden, B)};
+  if (const char* e = getenv("VCLA_CSK_SPLITS")) {            // tuning override: "qkv,o,gu,d,lm"
+    int o[5];
+    if (sscanf(e, "%d,%d,%d,%d,%d", &o[0], &o[1], &o[2], &o[3], &o[4]) == 5) for (int i = 0; i < 5; ++i) if (o[i] >= 1 && o[i] <= 8) v[i] = o[i];
+  }
+  c->csk_qkv = v[0]; c->csk_o = v[1]; c->csk_gu = v[2]; c->csk_d = v[3]; c->csk_lm = v[4];
+  c->csk_batch = B;
+  return 0;
+}
+
+static int decode_enqueue_csk(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
+  const vcla_config& g = c->cfg;
+  const int TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
+  const int slots = (TH + 127) / 128;                            // per-row sum-of-squares slots = 128-row tiles of the o / down projections
+  const float inv_dim = 1.0f / (float)TH;
+  count(c); if (dec_embed(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, c->tl[0].ln1, g.t_eps, c->d_xn, nullptr, c->d_ssq, slots, st)) return -1;
+  const float scale = 1.0f / sqrtf(128.f);
+  auto base = [&](const bf16* W, const bf16* X, int M, int K, int splits, int mode) {
+    CskCall k; k.W = W; k.X = X; k.M = M; k.B = B; k.K = K; k.splits = splits; k.mode = mode; k.inv_dim = inv_dim; k.eps = g.t_eps;
+    return k;
+  };
+  for (int i = 0; i < g.t_layers; ++i) {
+    const TextLayer& L = c->tl[i];
+    { CskCall k = base(L.wqkv, c->d_xn, 3 * TH, TH, c->csk_qkv, CSK_OUT_F32); k.out = c->ws_qkv; k.ldo = 3 * TH; k.ssq_in = c->d_ssq; k.ssq_slots = slots;
+      count(c); if (gemm_csk(k, st)) return -1; }
+    DecodeAttnCall a; a.qkv_partial = c->ws_qkv; a.splits = 1; a.ws_rows = B; a.kv_pages = L.kv; a.page_table = c->page_table;
+    a.pages_per_seq = c->pages_per_seq; a.page_tokens = c->page_tokens; a.seq_len = c->seq_len; a.out = c->d_attn; a.scratch = c->attn_scratch;
+    a.counters = c->attn_counters; a.B = B; a.H = H; a.HD = 128; a.scale = scale; a.rope_theta = g.rope_theta;
+    a.rope_cos = c->rope_cos; a.rope_sin = c->rope_sin; a.persistent_mode = c->attn_persistent_mode; a.persistent_grid = c->attn_persistent_grid;
+    { int want = (num_sms() + B * H - 1) / (B * H); int ks = want > c->kv_splits ? want : c->kv_splits; a.kv_splits = ks > 8 ? 8 : ks; }
+    count(c); if (attention_decode(a, st)) return -1;
+    { CskCall k = base(L.wo, c->d_attn, TH, TH, c->csk_o, CSK_RESID); k.resid = c->d_resid; k.norm_w = L.ln2; k.xw = c->d_xn; k.ssq_out = c->d_ssq;
+      count(c); if (gemm_csk(k, st)) return -1; }
+    { CskCall k = base(L.wgu, c->d_xn, 2 * F, TH, c->csk_gu, CSK_SWIGLU); k.h = c->d_h; k.ssq_in = c->d_ssq; k.ssq_slots = slots;
+      count(c); if (gemm_csk(k, st)) return -1; }
+    { CskCall k = base(L.wd, c->d_h, TH, F, c->csk_d, CSK_RESID); k.resid = c->d_resid; k.norm_w = (i + 1 < g.t_layers) ? c->tl[i + 1].ln1 : c->final_norm;
+      k.xw = c->d_xn; k.ssq_out = c->d_ssq;
+      count(c); if (gemm_csk(k, st)) return -1; }
+  }
+  { CskCall k = base(c->lm_head, c->d_xn, g.t_vocab, TH, c->csk_lm, CSK_OUT_F32); k.out = c->ws_lm; k.ldo = g.t_vocab; k.ssq_in = c->d_ssq; k.ssq_slots = slots;
+    count(c); if (gemm_csk(k, st)) return -1; }
+  if (logits_argmax(c, B, logits, tok_out, nullptr, 1, st, 1)) return -1;
+  count(c); if (advance_and_reserve(c, B, st)) return -1;
+  return 0;
+}
+
 // Decode step, 5 kernels per layer:  QKV GEMM -> attention(+reduce, rstd, RoPE, append) -> O GEMM [+residual, norm weight, sum sq]
 //   -> gate/up GEMM [+rstd, SiLU*mul] -> down GEMM [+residual, next norm weight, sum sq].  The bracketed consumers run inside
 // the GEMM, in the CTA whose split-K partial completes a tile; RMSNorm's per-row scale is deferred to the next consumer.
 static int decode_enqueue(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, int32_t* tok_out, cudaStream_t st) {
+  if (c->decode_schedule == 2 && B <= 32) return decode_enqueue_csk(c, tok_in, B, logits, tok_out, st);
   if (!c->fused_decode) return decode_enqueue_unfused(c, tok_in, B, logits, tok_out, st);
   const vcla_config& g = c->cfg;
   const int TH = g.t_hidden, F = g.t_ffn, H = g.t_heads;
-  count(c); if (dec_embed(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, c->tl[0].ln1, g.t_eps, c->d_xn, c->d_rstd, st)) return -1;
+  count(c); if (dec_embed(tok_in, B, TH, c->embed, g.t_vocab, c->d_resid, c->tl[0].ln1, g.t_eps, c->d_xn, c->d_rstd, nullptr, 0, st)) return -1;
   const float scale = 1.0f / sqrtf(128.f);
   GemmFix fr;   // residual + deferred norm
   fr.mode = FIX_RESID; fr.resid = c->d_resid; fr.xw_out = c->d_xn; fr.ssq = c->d_ssq; fr.rstd_out = c->d_rstd; fr.inv_dim = 1.0f / (float)TH; fr.eps = g.t_eps;
@@ -962,6 +1083,7 @@ int vcla_decode_step(vcla_ctx* c, const int32_t* tok_in, int B, float* logits, i
   if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
   if (!tok_in || !tok_out) { set_error("decode: null token buffers"); return -1; }
   if (decode_capacity(c, 1)) return -1;
+  if (c->decode_schedule == 2 && B <= 32 && csk_prepare(c, B)) return -1;      // occupancy queries: never inside a capture
   int rc = use_graph ? decode_graph(c, tok_in, B, logits, tok_out, 1, st) : decode_enqueue(c, tok_in, B, logits, tok_out, st);
   if (rc == 0 && !use_graph && c->dp_on()) rc = dp_wait(c, st);
   if (rc == 0) c->len_bound += 1;
@@ -974,6 +1096,7 @@ int vcla_decode_multi(vcla_ctx* c, int32_t* tok_inout, int B, int n_steps, vcla_
   if (B < 1 || B > c->cfg.max_batch || B > 64) { set_error("decode: batch %d unsupported", B); return -1; }
   if (!tok_inout || n_steps < 1 || n_steps > 64) { set_error("decode_multi: bad arguments"); return -1; }
   if (decode_capacity(c, n_steps)) return -1;
+  if (c->decode_schedule == 2 && B <= 32 && csk_prepare(c, B)) return -1;
   const int rc = decode_graph(c, tok_inout, B, nullptr, tok_inout, n_steps, (cudaStream_t)stream);
   if (rc == 0) c->len_bound += n_steps;
   return rc;
@@ -1128,7 +1251,24 @@ int vcla_bench_decode_gemm(vcla_ctx* c, int which, int B, int reps, float* avg_u
   cudaEvent_t e0, e1;
   VCLA_CUDA_OK(cudaEventCreate(&e0));
   VCLA_CUDA_OK(cudaEventCreate(&e1));
+  const bool csk = c->decode_schedule == 2 && B <= 32;
+  if (csk && csk_prepare(c, B)) return -1;
+  const int slots = (TH + 127) / 128;
+  auto csk_one = [&](int w, const TextLayer* L) -> int {
+    CskCall k; k.B = B; k.inv_dim = 1.0f / (float)TH; k.eps = g.t_eps;
+    if (w == 0) { k.W = L->wqkv; k.X = c->d_xn; k.M = 3 * TH; k.K = TH; k.splits = c->csk_qkv; k.mode = CSK_OUT_F32; k.out = c->ws_qkv; k.ldo = 3 * TH; k.ssq_in = c->d_ssq; k.ssq_slots = slots; }
+    if (w == 1) { k.W = L->wo; k.X = c->d_attn; k.M = TH; k.K = TH; k.splits = c->csk_o; k.mode = CSK_RESID; k.resid = c->d_resid; k.norm_w = L->ln2; k.xw = c->d_xn; k.ssq_out = c->d_ssq; }
+    if (w == 2) { k.W = L->wgu; k.X = c->d_xn; k.M = 2 * F; k.K = TH; k.splits = c->csk_gu; k.mode = CSK_SWIGLU; k.h = c->d_h; k.ssq_in = c->d_ssq; k.ssq_slots = slots; }
+    if (w == 3) { k.W = L->wd; k.X = c->d_h; k.M = TH; k.K = F; k.splits = c->csk_d; k.mode = CSK_RESID; k.resid = c->d_resid; k.norm_w = L->ln1; k.xw = c->d_xn; k.ssq_out = c->d_ssq; }
+    if (w == 4) { k.W = c->lm_head; k.X = c->d_xn; k.M = g.t_vocab; k.K = TH; k.splits = c->csk_lm; k.mode = CSK_OUT_F32; k.out = c->ws_lm; k.ldo = g.t_vocab; k.ssq_in = c->d_ssq; k.ssq_slots = slots; }
+    count(c); return gemm_csk(k, st);
+  };
   auto run_all = [&]() -> int {
+    if (csk) {
+      if (which == 4) return csk_one(4, nullptr);
+      for (int i = 0; i < g.t_layers; ++i) if (csk_one(which, &c->tl[i])) return -1;
+      return 0;
+    }
     if (which == 4) return swap_gemm(c, c->lm_head, g.t_vocab, TH, c->d_xn, B, c->sp_lm, c->ws_lm, st);
     for (int i = 0; i < g.t_layers; ++i) {
       const TextLayer& L = c->tl[i];

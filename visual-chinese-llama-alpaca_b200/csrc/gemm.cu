@@ -65,6 +65,9 @@ struct GemmParams {
   int l2_prefetch_kb;
   uint64_t policy_a, policy_b;
   GemmFix fix;
+  GemmRowScale rowscale;
+  GemmEmitNorm emit;
+  GemmRope rope;
 };
 
 constexpr int kBlockM = 128;
@@ -400,7 +403,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int orow = row;
         if (p.rows_per_group > 0) orow = (row / p.rows_per_group) * p.group_stride + (row % p.rows_per_group) + p.row_offset;
         const int col_tile = n_blk * BN;
-        if (p.mode == GEMM_SWIGLU_BF16) {
+        // deferred RMSNorm: the operand rows were not normalised; their scale commutes with the GEMM and lands here
+        float rs = 1.f;
+        if (p.rowscale.ssq != nullptr && row_ok) {
+          const float* sp = p.rowscale.ssq + (size_t)row * p.rowscale.slots;
+          float ss = 0.f;
+          for (int i = 0; i < p.rowscale.slots; ++i) ss += __ldg(sp + i);       // fixed order: deterministic
+          rs = rsqrtf(ss * p.rowscale.inv_dim + p.rowscale.eps);
+        }
+        if (p.rope.cos != nullptr) {
+          // ---- fused QKV epilogue: RoPE on q / k heads, store q|k|v rows, append k / v to the paged cache (BN = 256 = 2 heads)
+          if constexpr (BN == 256) {
+            const GemmRope& R = p.rope;
+            const int bq = row_ok ? row / R.S : 0, sq = row_ok ? row % R.S : 0;
+            const int pad = (R.left_pad != nullptr && row_ok) ? __ldg(R.left_pad + bq) : 0;
+            const int cpos = sq - pad;                               // index inside the (compact) KV cache
+            const bool cached = row_ok && cpos >= 0;                 // padding rows are neither rotated nor cached
+            const int pos = R.pos_from_mask ? (cpos > 0 ? cpos : 0) : sq;
+            int page = 0, slot = 0;
+            if (cached) { page = __ldg(R.page_table + (size_t)bq * R.pages_per_seq + cpos / R.page_tokens); slot = cpos % R.page_tokens; }
+            const float* ct = R.cos + (size_t)pos * 64;
+            const float* stb = R.sin + (size_t)pos * 64;
+            bf16* orow_ptr = reinterpret_cast<bf16*>(p.out) + (size_t)orow * p.ldo;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+              const int hcol = col_tile + hh * 128;                  // first column of this head inside [q | k | v]
+              if (hcol >= p.N) break;
+              const int region = hcol / R.T, head = (hcol % R.T) / 128;
+#pragma unroll 1
+              for (int half = 0; half < 2; ++half) {                 // dims [32 half, 32 half + 32) pair with [64 + 32 half, ...)
+                uint32_t lo[32], hi[32];
+                tmem_ld_32x32(taddr0 + hh * 128 + half * 32, lo);
+                tmem_ld_32x32(taddr0 + hh * 128 + 64 + half * 32, hi);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                uint32_t plo[16], phi[16];
+                if (region < 2 && cached) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct + half * 32) + i);
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(stb + half * 32) + i);
+                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+                    float ol[4], oh[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float a = __uint_as_float(lo[4 * i + j]) * rs, b2 = __uint_as_float(hi[4 * i + j]) * rs;
+                      ol[j] = a * cc[j] - b2 * sn[j];
+                      oh[j] = b2 * cc[j] + a * sn[j];
+                    }
+                    plo[2 * i] = pack_bf16x2(ol[0], ol[1]); plo[2 * i + 1] = pack_bf16x2(ol[2], ol[3]);
+                    phi[2 * i] = pack_bf16x2(oh[0], oh[1]); phi[2 * i + 1] = pack_bf16x2(oh[2], oh[3]);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    plo[i] = pack_bf16x2(__uint_as_float(lo[2 * i]) * rs, __uint_as_float(lo[2 * i + 1]) * rs);
+                    phi[i] = pack_bf16x2(__uint_as_float(hi[2 * i]) * rs, __uint_as_float(hi[2 * i + 1]) * rs);
+                  }
+                }
+                uint4* d0 = reinterpret_cast<uint4*>(orow_ptr + hcol + half * 32);
+                uint4* d1 = reinterpret_cast<uint4*>(orow_ptr + hcol + 64 + half * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  d0[i] = make_uint4(plo[4 * i], plo[4 * i + 1], plo[4 * i + 2], plo[4 * i + 3]);
+                  d1[i] = make_uint4(phi[4 * i], phi[4 * i + 1], phi[4 * i + 2], phi[4 * i + 3]);
+                }
+                if (region >= 1 && cached) {
+                  bf16* cdst = R.kv_pages + ((((size_t)page * 2 + (region - 1)) * R.H + head) * R.page_tokens + slot) * 128;
+                  uint4* c0 = reinterpret_cast<uint4*>(cdst + half * 32);
+                  uint4* c1 = reinterpret_cast<uint4*>(cdst + 64 + half * 32);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    c0[i] = make_uint4(plo[4 * i], plo[4 * i + 1], plo[4 * i + 2], plo[4 * i + 3]);
+                    c1[i] = make_uint4(phi[4 * i], phi[4 * i + 1], phi[4 * i + 2], phi[4 * i + 3]);
+                  }
+                }
+              }
+            }
+          }
+        } else if (p.mode == GEMM_SWIGLU_BF16) {
           if constexpr (BN % 64 == 0) {
             bf16* out = reinterpret_cast<bf16*>(p.out);
 #pragma unroll 1
@@ -414,8 +495,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  float g0 = __uint_as_float(g[2 * i]), g1 = __uint_as_float(g[2 * i + 1]);
-                  float u0 = __uint_as_float(u[2 * i]), u1 = __uint_as_float(u[2 * i + 1]);
+                  float g0 = __uint_as_float(g[2 * i]) * rs, g1 = __uint_as_float(g[2 * i + 1]) * rs;
+                  float u0 = __uint_as_float(u[2 * i]) * rs, u1 = __uint_as_float(u[2 * i + 1]) * rs;
                   float h0 = g0 / (1.f + __expf(-g0)) * u0;
                   float h1 = g1 / (1.f + __expf(-g1)) * u1;
                   pk[i] = pack_bf16x2(h0, h1);
@@ -427,6 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
+          float ssq_acc = 0.f;     // GemmEmitNorm: this tile's share of the row's sum of squares
 #pragma unroll 1
           for (int c = 0; c < BN / C::CH; ++c) {
             uint32_t v[C::CH];
@@ -438,7 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool full = (col0 + C::CH <= p.N);
             float x[C::CH];
 #pragma unroll
-            for (int i = 0; i < C::CH; ++i) x[i] = __uint_as_float(v[i]);
+            for (int i = 0; i < C::CH; ++i) x[i] = __uint_as_float(v[i]) * rs;
             if (p.bias != nullptr) {
               if (full) {
                 const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
@@ -485,6 +567,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                   }
                   dst[i] = o;
+                  if (p.emit.xw != nullptr) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.emit.norm_w + col0) + i);
+                    ssq_acc += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+                    *reinterpret_cast<uint2*>(p.emit.xw + (size_t)orow * p.emit.ldxw + col0 + 4 * i) =
+                        make_uint2(pack_bf16x2(o.x * w4.x, o.y * w4.y), pack_bf16x2(o.z * w4.z, o.w * w4.w));
+                  }
                 }
               } else {
 #pragma unroll
@@ -494,11 +582,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (rt) o += __ldg(rt + i);
                     if (p.accumulate) o += out[i];
                     out[i] = o;
+                    if (p.emit.xw != nullptr) {
+                      ssq_acc += o * o;
+                      p.emit.xw[(size_t)orow * p.emit.ldxw + col0 + i] = __float2bfloat16(o * __ldg(p.emit.norm_w + col0 + i));
+                    }
                   }
                 }
               }
             }
           }
+          if (p.emit.ssq_out != nullptr && row_ok) p.emit.ssq_out[(size_t)orow * p.n_tiles + n_blk] = ssq_acc;
         }
       }
       // release this accumulator stage back to the MMA warp
@@ -607,6 +700,16 @@ static int launch(const GemmCall& c, GemmParams p, cudaStream_t st) {
   return 0;
 }
 
+// tile width of a non-swap GEMM with M rows and N output columns (the widest tile that still gives every SM work)
+int gemm_pick_bn(int M, int N) {
+  const long m_tiles = (M + kBlockM - 1) / kBlockM;
+  const long tiles256 = m_tiles * ((N + 255) / 256);
+  const long tiles128 = m_tiles * ((N + 127) / 128);
+  if (tiles256 >= num_sms() || N >= 4096) return 256;
+  if (tiles128 >= num_sms() / 2 || N > 64) return 128;
+  return 64;
+}
+
 int gemm_tc(const GemmCall& c, cudaStream_t st) {
   if (gemm_init()) return -1;
   if (c.M <= 0 || c.N <= 0 || c.K <= 0) { set_error("gemm: empty problem"); return -1; }
@@ -623,6 +726,7 @@ int gemm_tc(const GemmCall& c, cudaStream_t st) {
   p.ws_rows = c.ws_rows;
   p.l2_prefetch_kb = c.l2_prefetch_kb;
   p.fix = c.fix;
+  p.rowscale = c.rowscale; p.emit = c.emit; p.rope = c.rope;
   p.policy_a = c.weights_are_A ? kEvictFirst : kEvictLast;
   p.policy_b = c.weights_are_A ? kEvictLast : kEvictNormal;
 
@@ -642,15 +746,13 @@ int gemm_tc(const GemmCall& c, cudaStream_t st) {
   p.splits = 1;
   p.kb_per_split = p.kb_total;
   if (c.mode == GEMM_SWIGLU_BF16 && (c.N % 64) != 0) { set_error("gemm: SwiGLU needs N %% 64 == 0 (N=%d)", c.N); return -1; }
-  int bn = c.bn;
-  if (bn == 0) {
-    // pick the widest tile that still gives every SM work
-    const long tiles256 = (long)p.m_tiles * ((c.N + 255) / 256);
-    const long tiles128 = (long)p.m_tiles * ((c.N + 127) / 128);
-    if (tiles256 >= num_sms() || c.N >= 4096) bn = 256;
-    else if (tiles128 >= num_sms() / 2 || c.N > 64) bn = 128;
-    else bn = 64;
+  if (c.emit.xw != nullptr && !(c.mode == GEMM_ADD_F32 && c.accumulate && c.emit.norm_w && c.emit.ssq_out)) { set_error("gemm: emit-norm needs ADD_F32 + accumulate + norm_w + ssq_out"); return -1; }
+  if (c.rope.cos != nullptr && !(c.mode == GEMM_STORE_BF16 && c.N == 3 * c.rope.T && c.rope.T % 128 == 0 && c.bias == nullptr && c.act == ACT_NONE && c.rows_per_group == 0 && (c.ldo % 8) == 0)) {
+    set_error("gemm: the RoPE + KV-append epilogue needs the plain fused QKV projection (N = 3T, T %% 128 == 0)"); return -1;
   }
+  int bn = c.bn;
+  if (c.rope.cos != nullptr) bn = 256;    // two whole heads per tile
+  if (bn == 0) bn = gemm_pick_bn(c.M, c.N);
   if (bn == 256) return launch<256, 4, false>(c, p, st);
   if (bn == 128) return launch<128, 6, false>(c, p, st);
   if (bn == 64) return launch<64, 8, false>(c, p, st);

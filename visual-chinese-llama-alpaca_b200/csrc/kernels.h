@@ -54,6 +54,30 @@ struct GemmFix {
   bf16* h_out = nullptr;              // [B, N_out/2]
 };
 
+// ---- prefill epilogue fusions (non-swap GEMMs) --------------------------------------------------------------------------
+// Deferred RMSNorm: the A operand holds xw = bf16(resid * norm_w) (NOT normalised); the row scale rstd[row] =
+// rsqrt(sum_slots ssq[row][slot] / dim + eps) commutes with the GEMM and is applied to the accumulator in the epilogue.
+struct GemmRowScale {
+  const float* ssq = nullptr;   // [M][slots] partial sums of squares of the fp32 residual rows (written by the producing GEMM)
+  int slots = 0;
+  float inv_dim = 0.f, eps = 0.f;
+};
+// GEMM_ADD_F32 + accumulate: besides resid += acc, emit the NEXT GEMM's operand and the row statistics:
+//   xw[orow, col] = bf16(resid_new * norm_w[col]) ; ssq_out[orow][n_blk] = sum over this tile's columns of resid_new^2
+struct GemmEmitNorm {
+  const float* norm_w = nullptr;   // [N]
+  bf16* xw = nullptr; int ldxw = 0;
+  float* ssq_out = nullptr;        // [M][n_tiles]
+};
+// GEMM_STORE_BF16 on the fused QKV projection [M, 3T]: rotate q and k heads (HF rotate_half pairs d, d+64; fp32 tables
+// [pos][64]) on the fp32 accumulator, store q|k|v rows (the prefill attention reads them) AND append k, v to the paged KV cache.
+struct GemmRope {
+  const float* cos = nullptr; const float* sin = nullptr;
+  bf16* kv_pages = nullptr; const int32_t* page_table = nullptr; int pages_per_seq = 0, page_tokens = 0;
+  int S = 0, T = 0, H = 0;                     // rows per sequence, hidden size (= H * 128), heads
+  const int32_t* left_pad = nullptr; int pos_from_mask = 0;
+};
+
 struct GemmCall {
   const bf16* A = nullptr;   // [M, K], row pitch lda elements
   const bf16* B = nullptr;   // [N, K], row pitch ldb elements
@@ -78,11 +102,37 @@ struct GemmCall {
   int bn = 0;                // tile N override (0 = auto)
   int l2_prefetch_kb = 0;    // k-blocks of the weight operand each CTA prefetches into L2 while it waits for its dependency
   GemmFix fix;               // fused consumer of the split-K partials (decode)
+  GemmRowScale rowscale;     // deferred RMSNorm scale of the A rows (STORE_BF16 / SWIGLU_BF16)
+  GemmEmitNorm emit;         // ADD_F32 + accumulate: also write the next operand + row statistics
+  GemmRope rope;             // STORE_BF16: RoPE + KV-cache append (needs BN = 256, N = 3T)
 };
 int gemm_tc(const GemmCall& c, cudaStream_t st);
+int gemm_pick_bn(int M, int N);   // tile width gemm_tc picks for a non-swap GEMM (= the number of ssq slots per row it emits: ceil(N / bn))
 // correctness reference for the tests only (CUDA-core, one thread per output)
 int gemm_naive(const GemmCall& c, cudaStream_t st);
 int gemm_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
+
+// ------------------------------------------------------------------------------------------
+// decode GEMM with the split-K reduction inside a thread-block cluster (gemm_decode.cu)
+//   out[b, n] = sum_k W[n, k] * X[b, k]   W [M = N_out, K] bf16 (streamed), X [B <= 32, K] bf16
+// ------------------------------------------------------------------------------------------
+enum CskMode {
+  CSK_OUT_F32 = 0,   // out[b * ldo + n] = rstd[b] * acc
+  CSK_RESID = 1,     // resid[b, n] += acc ; xw[b, n] = bf16(resid * norm_w[n]) ; ssq_out[b, n / 128] = sum over the tile of resid^2
+  CSK_SWIGLU = 2,    // W rows interleaved [32 gate | 32 up]: h[b, j] = bf16(silu(rstd[b] * g) * (rstd[b] * u))
+};
+struct CskCall {
+  const bf16* W = nullptr; const bf16* X = nullptr;
+  int M = 0, B = 0, K = 0;
+  int splits = 1;                       // CTAs per cluster = K slices (1..8, every slice non-empty)
+  int mode = CSK_OUT_F32;
+  float* out = nullptr; int ldo = 0;
+  float* resid = nullptr; const float* norm_w = nullptr; bf16* xw = nullptr; float* ssq_out = nullptr;
+  bf16* h = nullptr;
+  const float* ssq_in = nullptr; int ssq_slots = 0; float inv_dim = 0.f, eps = 0.f;   // rstd[b] = rsqrt(sum_slots ssq_in[b][slot] * inv_dim + eps); null: 1
+};
+int gemm_csk(const CskCall& c, cudaStream_t st);
+int gemm_csk_clusters(int B, int splits);   // clusters of `splits` CTAs that can be co-resident (occupancy query, cached)
 int trace_set_gemm(void* buf, unsigned long long cap);
 int trace_set_attention(void* buf, unsigned long long cap);
 int trace_set_elementwise(void* buf, unsigned long long cap);
@@ -130,6 +180,8 @@ int attention_init();          // sets the dynamic-smem attributes and reads the
 int layernorm(const float* x, int rows, int D, const float* w, const float* b, float eps, bf16* y_bf16, float* y_f32,
               cudaStream_t st);
 int rmsnorm(const float* x, int rows, int D, const float* w, float eps, bf16* y_bf16, cudaStream_t st);
+// head of the deferred-norm chain: xw = bf16(x * w) (not normalised), ssq[row][0] = sum x^2, ssq[row][1..slots) = 0
+int prenorm_rows(const float* x, int rows, int D, const float* w, bf16* xw, float* ssq, int slots, cudaStream_t st);
 // pixels (B,3,I,I) in f32/f16/bf16 -> im2col rows [B*g*g, Kpad] bf16 (k = c*P*P + ky*P + kx), zero padded
 int im2col(const void* pixels, int dtype, int B, int image, int patch, int kpad, bf16* out, cudaStream_t st);
 // hidden[b, 0, :] = cls + pos[0]
@@ -185,9 +237,10 @@ int sampler_init();
 int dec_sample(const float* logits, int ld, int V, int B, const int32_t* history, const int32_t* step_idx, const SamplerParams* params_dev,
                int32_t* tok, int32_t* history_out, int32_t* dp_send, int32_t* finished, float* scores_out, cudaStream_t st);
 int dp_unpack(const int32_t* recv, int n, int32_t* hist, int32_t* dp_step, cudaStream_t st);
-// decode step entry: resid[b,:] = table[ids[b]] ; xw = bf16(resid * norm_w) ; rstd[b] = rsqrt(mean(resid^2) + eps)
+// decode step entry: resid[b,:] = table[ids[b]] ; xw = bf16(resid * norm_w) ; rstd[b] = rsqrt(mean(resid^2) + eps) (nullable) ;
+// ssq[b][0] = sum resid^2, ssq[b][1..slots) = 0 (nullable: head of the deferred-norm chain of the cluster split-K schedule)
 int dec_embed(const int32_t* ids, int B, int D, const bf16* table, int vocab, float* resid, const float* norm_w, float eps,
-              bf16* xw, float* rstd, cudaStream_t st);
+              bf16* xw, float* rstd, float* ssq, int slots, cudaStream_t st);
 // ---- device-side KV page allocator (stream-ordered, graph-capturable; one thread walks the <= 64 sequences, so the
 //      assignment is deterministic) ------------------------------------------------------------------------------
 // kv_state[0] = free pages, kv_state[1] = error flag (pool exhausted); kv_free = stack of free physical pages;
