@@ -214,6 +214,17 @@ int vcla_read_stage(vcla_ctx* ctx, const char* stage, int B, float* dst_host, vc
  * (out f32 [splits][M_b][N] with A = weights).  use_reference != 0 runs the naive CUDA-core kernel instead. */
 int vcla_op_gemm(const void* A_dev_bf16, const void* W_dev_bf16, int M, int N, int K, int mode, int act, int accumulate,
                  const float* bias_dev, void* out_dev, int ldo, int splits, int tile_n, int use_reference, vcla_stream stream);
+/* Decode GEMM with the split-K reduction inside a thread-block cluster (csrc/gemm_decode.cu): out[b, n] = sum_k W[n, k] X[b, k], W (M, K)
+ * bf16 streamed once, X (B <= 32, K) bf16, `splits` CTAs per cluster (1..8).  mode 0: out_or_resid = out f32 (B, M) = rstd[b] * acc;
+ * mode 1: out_or_resid = resid f32 (B, M) += acc, xw_or_h = bf16 (B, M) = resid * norm_w, ssq_out f32 (B, ceil(M / 128)) = per-tile sums of
+ * squares; mode 2: W rows interleaved [32 gate | 32 up], xw_or_h = h bf16 (B, M / 2) = silu(rstd * g) * (rstd * u).
+ * rstd[b] = rsqrt(sum_slots ssq_in[b][slot] * inv_dim + eps), 1 when ssq_in is NULL.  vcla_op_gemm_csk_clusters: co-resident clusters. */
+int vcla_op_gemm_csk(const void* W_dev_bf16, const void* X_dev_bf16, int M, int B, int K, int splits, int mode, float* out_or_resid,
+                     const float* norm_w, void* xw_or_h, float* ssq_out, const float* ssq_in, int ssq_slots, float inv_dim, float eps,
+                     vcla_stream stream);
+int vcla_op_gemm_csk_clusters(int B, int splits);
+/* CTA-pair (tcgen05 cta_group::2, 256 x 256) tiles for the 256-wide prefill GEMMs: on by default; 0 selects the single-CTA 128 x 256 tile */
+void vcla_set_gemm_two_cta(int on);
 int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1,
                       const void* v1, int kv1_stride, int n1, void* out, int o_stride, int B, int H, int Sq, int HD, float scale,
                       int causal, vcla_stream stream);

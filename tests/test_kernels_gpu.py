@@ -186,3 +186,86 @@ def test_layernorm_rmsnorm(lib, rows, D):
     torch.cuda.synchronize()
     ref = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
     assert (yb.float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# decode GEMM with the split-K reduction inside a thread-block cluster (csrc/gemm_decode.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _csk(lib, W, X, splits, mode, out_or_resid=None, norm_w=None, xw_or_h=None, ssq_out=None, ssq_in=None, slots=0, inv_dim=0.0, eps=0.0):
+    M, K = W.shape
+    B = X.shape[0]
+    _check(lib, lib.vcla_op_gemm_csk(_p(W), _p(X), M, B, K, splits, mode, _p(out_or_resid), _p(norm_w), _p(xw_or_h), _p(ssq_out), _p(ssq_in), slots,
+                                     inv_dim, eps, _stream()))
+    torch.cuda.synchronize()
+
+
+CSK_CASES = [(4096, 4096, 8, 8), (4096, 4096, 1, 8), (12288, 4096, 8, 6), (12288, 4096, 3, 3), (4096, 11008, 8, 8), (1003, 256, 5, 2), (4096, 4096, 16, 8),
+             (4096, 4096, 17, 8), (12288, 4096, 32, 5), (4096, 11008, 29, 7), (49958, 4096, 8, 3), (640, 1024, 13, 1)]
+
+
+@pytest.mark.parametrize("M,K,B,S", CSK_CASES)
+def test_csk_out_f32_with_deferred_scale(lib, M, K, B, S):
+    W, X = _rand((M, K), 1.0 / math.sqrt(K), 11), _rand((B, K), 1.0, 12)
+    slots = 7
+    ssq = torch.rand(B, slots, device="cuda") * 50.0
+    out = torch.full((B, M), float("nan"), device="cuda")
+    _csk(lib, W, X, S, 0, out_or_resid=out, ssq_in=ssq, slots=slots, inv_dim=1.0 / K, eps=1e-6)
+    rstd = torch.rsqrt(ssq.sum(1) / K + 1e-6)
+    ref = (X.float() @ W.float().t()) * rstd[:, None]
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
+    out2 = torch.empty_like(out)
+    _csk(lib, W, X, S, 0, out_or_resid=out2, ssq_in=ssq, slots=slots, inv_dim=1.0 / K, eps=1e-6)
+    assert torch.equal(out, out2), "fixed reduction order: bit-identical run to run"
+
+
+@pytest.mark.parametrize("M,K,B,S", [(4096, 4096, 8, 8), (4096, 11008, 8, 8), (4096, 4096, 32, 8), (1024, 2752, 5, 4), (4096, 11008, 19, 6)])
+def test_csk_residual_next_operand_and_row_statistics(lib, M, K, B, S):
+    W, X = _rand((M, K), 1.0 / math.sqrt(K), 13), _rand((B, K), 1.0, 14)
+    resid0 = torch.randn(B, M, device="cuda")
+    norm_w = torch.randn(M, device="cuda") * 0.1 + 1.0
+    resid = resid0.clone()
+    xw = torch.empty(B, M, dtype=torch.bfloat16, device="cuda")
+    tiles = (M + 127) // 128
+    ssq = torch.full((B, tiles), float("nan"), device="cuda")
+    _csk(lib, W, X, S, 1, out_or_resid=resid, norm_w=norm_w, xw_or_h=xw, ssq_out=ssq)
+    ref = resid0 + X.float() @ W.float().t()
+    assert (resid - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    assert (xw.float() - resid * norm_w).abs().max().item() <= 1e-2 * (resid * norm_w).abs().max().item()
+    want = torch.nn.functional.pad(resid, (0, tiles * 128 - M)).view(B, tiles, 128).pow(2).sum(-1)
+    assert (ssq - want).abs().max().item() <= 1e-4 * want.max().item()
+
+
+@pytest.mark.parametrize("F,K,B,S", [(11008, 4096, 8, 5), (11008, 4096, 32, 5), (1408, 512, 3, 2), (2752, 1024, 17, 4)])
+def test_csk_swiglu(lib, F, K, B, S):
+    g, u = _rand((F, K), 1.0 / math.sqrt(K), 15), _rand((F, K), 1.0 / math.sqrt(K), 16)
+    assert F % 32 == 0
+    W = torch.stack([g.view(F // 32, 32, K), u.view(F // 32, 32, K)], 1).reshape(2 * F, K).contiguous()     # [32 gate | 32 up] blocks
+    X = _rand((B, K), 1.0, 17)
+    ssq = torch.rand(B, 3, device="cuda") * 30.0
+    h = torch.empty(B, F, dtype=torch.bfloat16, device="cuda")
+    _csk(lib, W, X, S, 2, xw_or_h=h, ssq_in=ssq, slots=3, inv_dim=1.0 / K, eps=1e-6)
+    rstd = torch.rsqrt(ssq.sum(1) / K + 1e-6)[:, None]
+    ref = torch.nn.functional.silu((X.float() @ g.float().t()) * rstd) * ((X.float() @ u.float().t()) * rstd)
+    assert (h.float() - ref).abs().max().item() <= 1.5e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_two_cta_tiles_match_single_cta(lib):
+    """cta_group::2 (CTA pair, 256 x 256 tiles) vs the single-CTA 128 x 256 tile: same inputs, same epilogues, bit-identical outputs
+    (the K order of the accumulation is the same), odd tile counts and ragged edges included."""
+    for M, N, K in [(1024, 12288, 4096), (2056, 4096, 1024), (300, 1003, 640), (129, 512, 64)]:
+        A, W = _rand((M, K), 1.0, 21), _rand((N, K), 1.0 / math.sqrt(K), 22)
+        bias = torch.randn(N, device="cuda")
+        outs = []
+        for two in (1, 0):
+            lib.vcla_set_gemm_two_cta(two)
+            out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+            _gemm(lib, A, W, 0, bias=bias, out=out, ldo=N, tile_n=256)
+            base = torch.randn(M, N, generator=torch.Generator().manual_seed(3)).cuda()
+            acc = base.clone()
+            _gemm(lib, A, W, 1, accumulate=1, bias=bias, out=acc, ldo=N, tile_n=256)
+            outs.append((out, acc))
+        lib.vcla_set_gemm_two_cta(1)
+        ref = A.float() @ W.float().t() + bias
+        assert (outs[0][0].float() - ref).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (M, N, K)

@@ -1341,6 +1341,18 @@ int vcla_op_gemm(const void* A, const void* W, int M, int N, int K, int mode, in
   g.bias = bias; g.out = out; g.ldo = ldo; g.splits = splits; g.ws_rows = N; g.bn = tile_n; g.weights_are_A = (mode == GEMM_PARTIAL_F32);
   return use_reference ? gemm_naive(g, (cudaStream_t)stream) : gemm_tc(g, (cudaStream_t)stream);
 }
+int vcla_op_gemm_csk(const void* W, const void* X, int M, int B, int K, int splits, int mode, float* out_or_resid, const float* norm_w, void* xw_or_h,
+                     float* ssq_out, const float* ssq_in, int ssq_slots, float inv_dim, float eps, vcla_stream stream) {
+  CskCall k; k.W = (const bf16*)W; k.X = (const bf16*)X; k.M = M; k.B = B; k.K = K; k.splits = splits; k.mode = mode;
+  k.ssq_in = ssq_in; k.ssq_slots = ssq_slots; k.inv_dim = inv_dim; k.eps = eps;
+  if (mode == CSK_OUT_F32) { k.out = out_or_resid; k.ldo = M; }
+  else if (mode == CSK_RESID) { k.resid = out_or_resid; k.norm_w = norm_w; k.xw = (bf16*)xw_or_h; k.ssq_out = ssq_out; }
+  else if (mode == CSK_SWIGLU) { k.h = (bf16*)xw_or_h; }
+  else { set_error("vcla_op_gemm_csk: unknown mode %d", mode); return -1; }
+  return gemm_csk(k, (cudaStream_t)stream);
+}
+int vcla_op_gemm_csk_clusters(int B, int splits) { return gemm_csk_clusters(B, splits); }
+void vcla_set_gemm_two_cta(int on) { gemm_set_two_cta(on); }
 int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1, const void* v1,
                       int kv1_stride, int n1, void* out, int o_stride, int B, int H, int Sq, int HD, float scale, int causal, vcla_stream stream) {
   AttnCall a; a.q = (const bf16*)q; a.q_stride = q_stride; a.k0 = (const bf16*)k0; a.v0 = (const bf16*)v0; a.kv0_stride = kv0_stride; a.n0 = n0;

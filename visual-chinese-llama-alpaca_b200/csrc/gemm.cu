@@ -18,6 +18,7 @@
 
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -74,10 +75,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kGemmThreads = 192;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = kBlockM * kBlockK * 2;
-  static constexpr int B_BYTES = BN * kBlockK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * kBlockK * 2;            // a CTA pair splits the B tile's N rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int FIX_OFF = BAR_OFF + 256;             // [4 warps][64] fp32 cross-warp scratch + 1 flag of the split-K fixup
@@ -94,10 +95,18 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-template <int BN, int STAGES, bool SWAP>
+// CTAS = 2: a CTA PAIR (cluster (2,1,1), two SMs of one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA stages
+// its own 128 A rows and HALF of the B tile, the leader (cluster rank 0) issues the MMAs for both, each CTA's TMEM receives its 128
+// rows.  Per SM and k-block this halves the B bytes written to and read from shared memory, which is what bounds the 128 x 256
+// single-CTA tile (A 4 KB + B 8 KB per 128-cycle MMA against a 128 B/cycle crossbar that also takes the TMA writes).
+template <int BN, int STAGES, bool SWAP, int CTAS = 1>
 __global__ void __launch_bounds__(kGemmThreads, SWAP ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using C = GemmCfg<BN, STAGES>;
+  using C = GemmCfg<BN, STAGES, CTAS>;
+  static_assert(CTAS == 1 || (!SWAP && BN == 256), "the CTA-pair variant is the 256 x 256 prefill tile");
+  constexpr bool TWO = CTAS == 2;
+  const int crank = TWO ? (int)cluster_rank() : 0;
+  const bool leader = crank == 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -120,23 +129,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 4 * CTAS);      // the leader's MMA warp waits for the epilogue warps of BOTH CTAs
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) { if constexpr (TWO) tmem_alloc_2cta(tmem_slot, C::TMEM_COLS); else tmem_alloc(tmem_slot, C::TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_barrier();        // the peer's barriers exist before TMA / commits / arrives target them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // PDL: let the next kernel's CTAs become resident as soon as ours are (they only prefetch read-only weights and
   // then block in griddepcontrol.wait until this grid has completed), see the producer below.
   pdl_launch_dependents();
+  const int tile0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // a pair walks the pair-tiles together
+  const int tile_step = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   auto tile_coords = [&](int t, int& m_blk, int& n_blk, int& kb0, int& kb1, int& ks) {
+    if constexpr (TWO) {
+      const int m_pairs = (p.m_tiles + 1) >> 1;
+      m_blk = (t % m_pairs) * 2 + crank;       // this CTA's 128 rows of the pair's 256
+      n_blk = t / m_pairs;
+      ks = 0; kb0 = 0; kb1 = p.kb_total;
+      return;
+    }
     m_blk = t % p.m_tiles;
     int r = t / p.m_tiles;
     n_blk = r % p.n_tiles;
@@ -162,17 +181,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       auto flush_pending = [&]() {
         pdl_wait();
         trace.dep();
-        for (int i = 0; i < npend; ++i) tma_load_2d(pend_dst[i], act_map, pend_c0[i], pend_c1[i], pend_bar[i], act_policy);
+        for (int i = 0; i < npend; ++i) {
+          if constexpr (TWO) tma_load_2d_2cta(pend_dst[i], act_map, pend_c0[i], pend_c1[i], pend_bar[i], act_policy);
+          else tma_load_2d(pend_dst[i], act_map, pend_c0[i], pend_c1[i], pend_bar[i], act_policy);
+        }
         npend = 0;
         dep_ready = true;
       };
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tile_step) {
         int m_blk, n_blk, kb0, kb1, ks;
         tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const uint32_t sa = base + stage * C::STAGE_BYTES;
+          if constexpr (TWO) {
+            // both CTAs' bytes are counted on the LEADER's full barrier (the only one the MMA thread waits on)
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            tma_load_2d_2cta(sa + C::A_BYTES, &tmB, kb * kBlockK, n_blk * BN + crank * (BN / 2), full_bar(stage), p.policy_b);   // weights (half)
+            if (dep_ready) {
+              tma_load_2d_2cta(sa, &tmA, kb * kBlockK, m_blk * kBlockM, full_bar(stage), p.policy_a);
+            } else {
+              pend_dst[npend] = sa; pend_bar[npend] = full_bar(stage); pend_c0[npend] = kb * kBlockK; pend_c1[npend] = m_blk * kBlockM; ++npend;
+            }
+            if (!dep_ready && npend == STAGES) flush_pending();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           if constexpr (SWAP) {
             tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * kBlockM, full_bar(stage), p.policy_a);           // weights
             if (dep_ready) {
@@ -213,14 +248,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN);
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (CTA pair: the leader only) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CTAS, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t accphase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < p.total_tiles; t += tile_step) {
         int m_blk, n_blk, kb0, kb1, ks;
         tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
         mbar_wait(tempty_bar(acc), accphase ^ 1u);
@@ -235,12 +270,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the 16 B-unit address field
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (TWO) umma_bf16_2cta(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (pair: the slot of BOTH CTAs)
+          if constexpr (TWO) umma_commit_2cta(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: each CTA's epilogue reads its own TMEM)
+        if constexpr (TWO) umma_commit_2cta(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) accphase ^= 1u;
       }
@@ -253,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();                            // outputs / residual reads are ordered after the previous grid
     int acc = 0;
     uint32_t accphase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = tile0; t < p.total_tiles; t += tile_step) {
       int m_blk, n_blk, kb0, kb1, ks;
       tile_coords(t, m_blk, n_blk, kb0, kb1, ks);
       mbar_wait(tfull_bar(acc), accphase);
@@ -594,10 +632,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.emit.ssq_out != nullptr && row_ok) p.emit.ssq_out[(size_t)orow * p.n_tiles + n_blk] = ssq_acc;
         }
       }
-      // release this accumulator stage back to the MMA warp
+      // release this accumulator stage back to the MMA warp (pair: the leader's)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (TWO && !leader) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
     }
@@ -605,8 +643,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_barrier();        // the peer may still address this CTA's barriers / shared memory / TMEM
   trace.done();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == 1) { if constexpr (TWO) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS); }
 }
 
 VCLA_DEFINE_TRACE_SETTER(trace_set_gemm)
@@ -621,10 +660,10 @@ static PFN_encodeTiled g_encode = nullptr;
 static std::once_flag g_gemm_once;
 static int g_gemm_init_rc = 0;
 
-template <int BN, int STAGES, bool SWAP>
+template <int BN, int STAGES, bool SWAP, int CTAS = 1>
 static int set_attr() {
-  using C = GemmCfg<BN, STAGES>;
-  VCLA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  using C = GemmCfg<BN, STAGES, CTAS>;
+  VCLA_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, SWAP, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   return 0;
 }
 
@@ -639,6 +678,7 @@ static int gemm_init_impl() {
   }
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   if (set_attr<256, 4, false>()) return -1;
+  if (set_attr<256, 6, false, 2>()) return -1;
   if (set_attr<128, 6, false>()) return -1;
   if (set_attr<64, 8, false>()) return -1;
   if (set_attr<16, 5, true>()) return -1;
@@ -671,24 +711,29 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
   return 0;
 }
 
-template <int BN, int STAGES, bool SWAP>
+template <int BN, int STAGES, bool SWAP, int CTAS = 1>
 static int launch(const GemmCall& c, GemmParams p, cudaStream_t st) {
-  using C = GemmCfg<BN, STAGES>;
+  using C = GemmCfg<BN, STAGES, CTAS>;
   CUtensorMap ta, tb;
   if (make_tmap(&ta, c.A, c.M, c.K, c.lda, kBlockM)) return -1;
-  if (make_tmap(&tb, c.B, c.N, c.K, c.ldb, BN)) return -1;
+  if (make_tmap(&tb, c.B, c.N, c.K, c.ldb, BN / CTAS)) return -1;
   p.n_tiles = (c.N + BN - 1) / BN;
-  p.total_tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int slots = num_sms() * (SWAP ? 2 : 1);
-  const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+  p.total_tiles = (CTAS == 2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;     // pair-tiles of 256 rows
+  const int slots = CTAS == 2 ? num_sms() / 2 : num_sms() * (SWAP ? 2 : 1);
+  const int grid = (p.total_tiles < slots ? p.total_tiles : slots) * CTAS;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int nattr = 0;
+  if (CTAS == 2) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = 2; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+  }
   if (pdl_enabled()) {
     attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[nattr].val.programmaticStreamSerializationAllowed = 1;
@@ -696,9 +741,17 @@ static int launch(const GemmCall& c, GemmParams p, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, SWAP>, ta, tb, p));
+  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, SWAP, CTAS>, ta, tb, p));
   return 0;
 }
+
+// CTA-pair tiles (cta_group::2): on by default for the 256-wide prefill tile; VCLA_GEMM_2CTA=0 keeps the single-CTA 128 x 256 tile
+static int g_two_cta = -1;
+static bool two_cta_enabled() {
+  if (g_two_cta < 0) { const char* e = getenv("VCLA_GEMM_2CTA"); g_two_cta = (e == nullptr) ? 1 : (atoi(e) != 0); }
+  return g_two_cta != 0;
+}
+void gemm_set_two_cta(int on) { g_two_cta = on ? 1 : 0; }
 
 // tile width of a non-swap GEMM with M rows and N output columns (the widest tile that still gives every SM work)
 int gemm_pick_bn(int M, int N) {
@@ -753,6 +806,7 @@ int gemm_tc(const GemmCall& c, cudaStream_t st) {
   int bn = c.bn;
   if (c.rope.cos != nullptr) bn = 256;    // two whole heads per tile
   if (bn == 0) bn = gemm_pick_bn(c.M, c.N);
+  if (bn == 256 && two_cta_enabled() && p.m_tiles >= 2) return launch<256, 6, false, 2>(c, p, st);
   if (bn == 256) return launch<256, 4, false>(c, p, st);
   if (bn == 128) return launch<128, 6, false>(c, p, st);
   if (bn == 64) return launch<64, 8, false>(c, p, st);

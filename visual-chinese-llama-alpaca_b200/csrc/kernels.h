@@ -107,6 +107,7 @@ struct GemmCall {
   GemmRope rope;             // STORE_BF16: RoPE + KV-cache append (needs BN = 256, N = 3T)
 };
 int gemm_tc(const GemmCall& c, cudaStream_t st);
+void gemm_set_two_cta(int on);     // CTA-pair (cta_group::2) 256 x 256 tiles for the 256-wide prefill GEMMs (default on)
 int gemm_pick_bn(int M, int N);   // tile width gemm_tc picks for a non-swap GEMM (= the number of ssq slots per row it emits: ceil(N / bn))
 // correctness reference for the tests only (CUDA-core, one thread per output)
 int gemm_naive(const GemmCall& c, cudaStream_t st);

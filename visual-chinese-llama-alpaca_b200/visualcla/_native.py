@@ -70,6 +70,9 @@ _SIGNATURES = [
     ("vcla_kernel_launches", C.c_int64, [_P, C.c_int]),
     ("vcla_read_stage", C.c_int, [_P, C.c_char_p, C.c_int, _P, _P]),
     ("vcla_op_gemm", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    ("vcla_op_gemm_csk", C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_float, C.c_float, _P]),
+    ("vcla_op_gemm_csk_clusters", C.c_int, [C.c_int, C.c_int]),
+    ("vcla_set_gemm_two_cta", None, [C.c_int]),
     ("vcla_op_attention", C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     ("vcla_op_layernorm", C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P]),
