@@ -14,7 +14,7 @@ pdl = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 out_path = sys.argv[3] if len(sys.argv) > 3 else None
 N.load().vcla_set_pdl(pdl)
 TAGS = {1: "gemm_swap", 2: "gemm", 3: "attn_prefill", 4: "attn_decode", 5: "layernorm", 6: "rmsnorm", 7: "rope_cache", 8: "resid_norm",
-        9: "silu_mul", 10: "logits1", 11: "logits2", 12: "advance", 13: "embed"}
+        9: "silu_mul", 10: "logits1", 11: "logits2", 12: "advance", 13: "embed", 14: "sampler"}
 m = visualcla.VisualCLAModel.from_synthetic("7b", seed=0, max_batch=B, max_seq=400, max_prefill_tokens=B * 128)
 m.image_at_head = True
 eng = m._engine
@@ -51,5 +51,19 @@ for i, (tag, a, b, c) in enumerate(ev):
 # how early do kernels start relative to their predecessor's dependency resolution?
 early = [rows[i]["dep_us"] - rows[i]["entry_us"] for i in range(1, len(rows)) if rows[i]["dep_us"] is not None]
 print(f"mean (dep - entry) = {sum(early) / len(early):.2f} us  (time a kernel's CTA 0 is resident before its inputs are ready)")
+# in-situ duration of a kernel = its successor's dependency-resolved time - its own (the launch gap included): they add up to the step
+deps = [(r["kernel"], r["dep_us"]) for r in rows if r["dep_us"] is not None]
+deps.sort(key=lambda x: x[1])
+per = {}
+gi = 0
+for i in range(len(deps) - 1):
+    k = deps[i][0]
+    if k == "gemm_swap":
+        k = ["gemm_qkv", "gemm_o", "gemm_gate_up", "gemm_down"][gi % 4] if gi < 128 else "gemm_lm_head"
+        gi += 1
+    per.setdefault(k, []).append(deps[i + 1][1] - deps[i][1])
+print("in-situ mean us per kernel kind:", {k: round(sum(v) / len(v), 2) for k, v in per.items()})
+print("per layer (sum of the per-layer kernels):", round(sum(sum(v) / len(v) for k, v in per.items() if len(v) >= 32), 2), "us")
 if out_path:
-    json.dump({"B": B, "pdl": pdl, "event_us": e0.elapsed_time(e1) * 1000, "events": rows}, open(out_path, "w"))
+    json.dump({"B": B, "pdl": pdl, "event_us": e0.elapsed_time(e1) * 1000, "insitu_mean_us": {k: sum(v) / len(v) for k, v in per.items()},
+               "schedule": os.environ.get("VCLA_DECODE_SCHEDULE", "csk"), "events": rows}, open(out_path, "w"))
