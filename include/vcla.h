@@ -223,6 +223,9 @@ int vcla_op_gemm_csk(const void* W_dev_bf16, const void* X_dev_bf16, int M, int 
                      const float* norm_w, void* xw_or_h, float* ssq_out, const float* ssq_in, int ssq_slots, float inv_dim, float eps,
                      vcla_stream stream);
 int vcla_op_gemm_csk_clusters(int B, int splits);
+/* tuning hooks: read / override the CTAs-per-cluster of the five decode GEMM shapes {qkv, o, gate_up, down, lm_head} at batch B */
+int vcla_debug_set_csk_splits(vcla_ctx* ctx, int B, int qkv, int o, int gate_up, int down, int lm_head);
+int vcla_debug_get_csk_splits(vcla_ctx* ctx, int B, int* out5);
 /* CTA-pair (tcgen05 cta_group::2, 256 x 256) tiles for the 256-wide prefill GEMMs: on by default; 0 selects the single-CTA 128 x 256 tile */
 void vcla_set_gemm_two_cta(int on);
 int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1,

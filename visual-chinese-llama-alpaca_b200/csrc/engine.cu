@@ -504,7 +504,7 @@ void vcla_destroy(vcla_ctx* c) {
   if (c->dp_fork) cudaEventDestroy(c->dp_fork);
   if (c->dp_join) cudaEventDestroy(c->dp_join);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); }
+  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_gemm_decode(nullptr, 0); trace_set_sampler(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); }
   delete c;
 }
 
@@ -1308,13 +1308,13 @@ int vcla_read_history(vcla_ctx* c, int32_t* dst_dev, int B, int n_steps, vcla_st
 int vcla_trace_enable(vcla_ctx* c, int max_events) {
   // installs (max_events > 0) or removes (0) the timeline buffer every kernel's CTA 0 appends to
   VCLA_CUDA_OK(cudaDeviceSynchronize());
-  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); c->trace_buf = nullptr; c->trace_cap = 0; }
+  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_gemm_decode(nullptr, 0); trace_set_sampler(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); c->trace_buf = nullptr; c->trace_cap = 0; }
   if (max_events <= 0) return 0;
   const size_t bytes = 8 + (size_t)max_events * 32;
   VCLA_CUDA_OK(cudaMalloc(&c->trace_buf, bytes));
   VCLA_CUDA_OK(cudaMemset(c->trace_buf, 0, bytes));
   c->trace_cap = (unsigned long long)max_events;
-  if (trace_set_gemm(c->trace_buf, c->trace_cap) || trace_set_attention(c->trace_buf, c->trace_cap) || trace_set_elementwise(c->trace_buf, c->trace_cap)) {
+  if (trace_set_gemm(c->trace_buf, c->trace_cap) || trace_set_gemm_decode(c->trace_buf, c->trace_cap) || trace_set_sampler(c->trace_buf, c->trace_cap) || trace_set_attention(c->trace_buf, c->trace_cap) || trace_set_elementwise(c->trace_buf, c->trace_cap)) {
     set_error("vcla_trace_enable: cudaMemcpyToSymbol failed");
     return -1;
   }
@@ -1350,6 +1350,25 @@ int vcla_op_gemm_csk(const void* W, const void* X, int M, int B, int K, int spli
   else if (mode == CSK_SWIGLU) { k.h = (bf16*)xw_or_h; }
   else { set_error("vcla_op_gemm_csk: unknown mode %d", mode); return -1; }
   return gemm_csk(k, (cudaStream_t)stream);
+}
+int vcla_debug_set_csk_splits(vcla_ctx* c, int B, int qkv, int o, int gu, int d, int lm) {
+  // tuning hook: CTAs per cluster of the five decode GEMM shapes at batch B (0 = keep the automatic choice); drops the captured graphs
+  if (!c || B < 1 || B > 32) { set_error("vcla_debug_set_csk_splits: bad arguments"); return -1; }
+  c->csk_batch = 0;
+  if (csk_prepare(c, B)) return -1;
+  int* dst[5] = {&c->csk_qkv, &c->csk_o, &c->csk_gu, &c->csk_d, &c->csk_lm};
+  const int v[5] = {qkv, o, gu, d, lm};
+  for (int i = 0; i < 5; ++i) if (v[i] >= 1 && v[i] <= 8) *dst[i] = v[i];
+  VCLA_CUDA_OK(cudaDeviceSynchronize());
+  for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+  c->graphs.clear(); c->graph_launches.clear(); c->graph_lru.clear();
+  return 0;
+}
+int vcla_debug_get_csk_splits(vcla_ctx* c, int B, int* out5) {
+  if (!c || !out5 || B < 1 || B > 32) return -1;
+  if (c->csk_batch != B && csk_prepare(c, B)) return -1;
+  out5[0] = c->csk_qkv; out5[1] = c->csk_o; out5[2] = c->csk_gu; out5[3] = c->csk_d; out5[4] = c->csk_lm;
+  return 0;
 }
 int vcla_op_gemm_csk_clusters(int B, int splits) { return gemm_csk_clusters(B, splits); }
 void vcla_set_gemm_two_cta(int on) { gemm_set_two_cta(on); }

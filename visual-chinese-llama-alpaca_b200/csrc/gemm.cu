@@ -592,24 +592,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float* out = reinterpret_cast<float*>(p.out) + (size_t)orow * p.ldo + col0;
               const float* rt = p.rowtab ? p.rowtab + (size_t)(row % p.rowtab_period) * p.N + col0 : nullptr;
               if (full && (p.ldo & 3) == 0 && (p.N & 3) == 0) {
-                float4* dst = reinterpret_cast<float4*>(out);
+                // all loads first, then the arithmetic, then all stores: with the loads interleaved between stores to a second
+                // (possibly aliasing) output the compiler has to serialise one L2 round trip per float4
+                float4* __restrict__ dst = reinterpret_cast<float4*>(out);
+                float4 oldv[C::CH / 4];
+                if (p.accumulate) {
+#pragma unroll
+                  for (int i = 0; i < C::CH / 4; ++i) oldv[i] = dst[i];
+                }
 #pragma unroll
                 for (int i = 0; i < C::CH / 4; ++i) {
-                  float4 o = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
                   if (rt) {
-                    float4 r4 = __ldg(reinterpret_cast<const float4*>(rt) + i);
-                    o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(rt) + i);
+                    x[4 * i] += r4.x; x[4 * i + 1] += r4.y; x[4 * i + 2] += r4.z; x[4 * i + 3] += r4.w;
                   }
-                  if (p.accumulate) {
-                    float4 old = dst[i];
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                  }
-                  dst[i] = o;
-                  if (p.emit.xw != nullptr) {
-                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.emit.norm_w + col0) + i);
-                    ssq_acc += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
-                    *reinterpret_cast<uint2*>(p.emit.xw + (size_t)orow * p.emit.ldxw + col0 + 4 * i) =
-                        make_uint2(pack_bf16x2(o.x * w4.x, o.y * w4.y), pack_bf16x2(o.z * w4.z, o.w * w4.w));
+                  if (p.accumulate) { x[4 * i] += oldv[i].x; x[4 * i + 1] += oldv[i].y; x[4 * i + 2] += oldv[i].z; x[4 * i + 3] += oldv[i].w; }
+                }
+#pragma unroll
+                for (int i = 0; i < C::CH / 4; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                if (p.emit.xw != nullptr) {
+                  uint2* __restrict__ xd = reinterpret_cast<uint2*>(p.emit.xw + (size_t)orow * p.emit.ldxw + col0);
+                  const float4* __restrict__ wp = reinterpret_cast<const float4*>(p.emit.norm_w + col0);
+#pragma unroll
+                  for (int i = 0; i < C::CH / 4; ++i) {
+                    const float4 w4 = __ldg(wp + i);
+                    ssq_acc += x[4 * i] * x[4 * i] + x[4 * i + 1] * x[4 * i + 1] + x[4 * i + 2] * x[4 * i + 2] + x[4 * i + 3] * x[4 * i + 3];
+                    xd[i] = make_uint2(pack_bf16x2(x[4 * i] * w4.x, x[4 * i + 1] * w4.y), pack_bf16x2(x[4 * i + 2] * w4.z, x[4 * i + 3] * w4.w));
                   }
                 }
               } else {
@@ -741,6 +749,15 @@ static int launch(const GemmCall& c, GemmParams p, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
+  if (getenv("VCLA_DEBUG")) {
+    static bool once = false;
+    if (!once) {
+      once = true;
+      int per_sm = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_tc_kernel<BN, STAGES, SWAP, CTAS>, kGemmThreads, C::SMEM_BYTES);
+      fprintf(stderr, "[vcla] gemm_tc<%d,%d,%d,%d>: smem %d, occupancy query %d blocks/SM, grid %d\n", BN, STAGES, (int)SWAP, CTAS, C::SMEM_BYTES, per_sm, grid);
+    }
+  }
   VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, SWAP, CTAS>, ta, tb, p));
   return 0;
 }

@@ -22,6 +22,8 @@
 #include "kernels.h"
 
 #include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vcla {
@@ -41,9 +43,10 @@ struct CskParams {
   bf16* h;                     // SWIGLU: [B, M / 2]
   const float* ssq_in; int ssq_slots; float inv_dim, eps;   // deferred scale of the operand rows (null: 1)
   uint64_t policy_w, policy_x;
+  int cluster_fence;           // explicit fence.acq_rel.cluster before the remote arrive (VCLA_CSK_FENCE=1; the arrive itself is release.cluster)
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 struct CskCfg {
   static constexpr int A_BYTES = kCskBlockM * kCskBlockK * 2;
   static constexpr int B_BYTES = BN * kCskBlockK * 2;
@@ -51,7 +54,7 @@ struct CskCfg {
   static constexpr int RED_COLS = BN + 4;                                 // >= S * ceil(B / S) (checked at launch)
   static constexpr int RED_BYTES = RED_COLS * kCskBlockM * 4;             // one reduce buffer: [source][owned column][128 rows] fp32
   static constexpr int RED_OFF = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = RED_OFF + 2 * RED_BYTES;
+  static constexpr int BAR_OFF = RED_OFF + NBUF * RED_BYTES;        // NBUF = 2: double-buffered reduce; 1: one buffer + a 'consumed' barrier
   static constexpr int MISC_OFF = BAR_OFF + 256;                          // rstd[BN], ssq warp partials [4][BN], tmem slot
   static constexpr int SMEM_BYTES = MISC_OFF + 1024 + 1024;              // + slack for the 1024 B alignment of the ring
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : 64;
@@ -93,10 +96,10 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 __global__ void __launch_bounds__(kCskThreads, 2)
 gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const CskParams p) {
-  using C = CskCfg<BN, STAGES>;
+  using C = CskCfg<BN, STAGES, NBUF>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -128,7 +131,9 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();            // every peer's barriers exist before anybody arrives on them remotely
+  // Cluster rendezvous, split: everybody ARRIVES now (this CTA's barriers are initialised), only the epilogue warps WAIT, right before
+  // their first remote access -- the TMA producer starts streaming weights without waiting for the peers to become resident.
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -202,6 +207,7 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int cols_per = (p.B + S - 1) / S;         // batch columns owned by one CTA
     const int my_c0 = rank * cols_per;
     const int my_nc = max(0, min(cols_per, p.B - my_c0));
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every peer's reduce barriers exist from here on
     pdl_wait();                                     // everything below reads / writes buffers of the previous kernels
     // deferred RMSNorm scale of the operand rows
     for (int b = warp - 2; b < BN; b += 4) {
@@ -217,7 +223,11 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
     int acc = 0; uint32_t accphase = 0; int buf = 0; uint32_t redphase[2] = {0u, 0u};
+    // NBUF == 1: red_bar(1) counts, per tile, the S destinations that have consumed what this CTA delivered ("your slot in my buffer
+    // is free again"); the scatter of the next tile waits for it.  A deeper TMA ring fits in the shared memory this saves.
+    uint32_t freephase = 0u; bool first_tile = true;
     for (int t = cluster_id; t < p.m_tiles; t += p.n_clusters) {
+      const bool last_tile = t + p.n_clusters >= p.m_tiles;
       mbar_wait(tfull_bar(acc), accphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -228,6 +238,10 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));               // the MMA warp may start the next tile
+      if constexpr (NBUF == 1) {
+        if (!first_tile) { mbar_wait_cluster(red_bar(1), freephase); freephase ^= 1u; }
+        first_tile = false;
+      }
       // scatter: column c of this partial goes to CTA c / cols_per, slot [source = rank][c % cols_per][row]
       const uint32_t red_local = base + C::RED_OFF + (uint32_t)buf * C::RED_BYTES;
 #pragma unroll
@@ -238,7 +252,7 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           st_cluster_f32(mapa_u32(red_local + off, (uint32_t)dst), __uint_as_float(v[c]));
         }
       }
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      if (p.cluster_fence) asm volatile("fence.acq_rel.cluster;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");              // all 128 rows of this CTA's partial are written
       if (et < S) mbar_arrive_remote(mapa_u32(red_bar(buf), (uint32_t)et));   // release.cluster: publishes them to CTA `et`
       // gather: wait until all S sources have delivered the columns this CTA owns
@@ -295,18 +309,27 @@ gemm_csk_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           asm volatile("bar.sync 1, 128;" ::: "memory");          // s_part is reused by the next tile
         }
       }
-      buf ^= 1;
+      if constexpr (NBUF == 1) {
+        // every thread of this CTA is done reading the buffer: tell the S sources (never after the last tile: a peer may be gone)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!last_tile && et < S) mbar_arrive_remote(mapa_u32(red_bar(1), (uint32_t)et));
+      } else {
+        buf ^= 1;
+      }
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
     }
   }
 
+  // No closing cluster barrier: a CTA leaves its last reduce only after all S peers have delivered (and arrived on) its buffer, i.e.
+  // nobody addresses its shared memory afterwards, and every peer it wrote to is still waiting for exactly that delivery.
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();            // nobody exits while a peer may still write into its shared memory / arrive on its barriers
   trace.done();
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
+
+VCLA_DEFINE_TRACE_SETTER(trace_set_gemm_decode)
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -325,8 +348,14 @@ static int csk_init() {
       set_error("cuTensorMapEncodeTiled not available"); g_csk_rc = -1; return;
     }
     g_csk_encode = reinterpret_cast<PFN_encodeTiled>(fn);
-    if (cudaFuncSetAttribute(gemm_csk_kernel<16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CskCfg<16, 5>::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_csk_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CskCfg<32, 3>::SMEM_BYTES) != cudaSuccess) {
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory: ask for the maximum carve-out explicitly (the occupancy
+    // query for cluster launches otherwise assumes a carve-out that holds only one CTA)
+    auto prep = [](const void* fn, int bytes) {
+      return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+             cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    };
+    if (!prep((const void*)gemm_csk_kernel<16, 4, 2>, CskCfg<16, 4, 2>::SMEM_BYTES) || !prep((const void*)gemm_csk_kernel<32, 3, 2>, CskCfg<32, 3, 2>::SMEM_BYTES) ||
+        !prep((const void*)gemm_csk_kernel<16, 5, 1>, CskCfg<16, 5, 1>::SMEM_BYTES) || !prep((const void*)gemm_csk_kernel<32, 4, 1>, CskCfg<32, 4, 1>::SMEM_BYTES)) {
       set_error("gemm_csk: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError())); g_csk_rc = -1;
     }
   });
@@ -346,38 +375,50 @@ static int csk_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 }
 
 // clusters of S CTAs that can be co-resident (2 CTAs per SM, a cluster never spans GPCs), cached per (BN, S)
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 static int csk_max_clusters(int S) {
   static int cache[kCskMaxSplits + 1] = {0};
   if (cache[S] != 0) return cache[S];
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(S * 64); cfg.blockDim = dim3(kCskThreads); cfg.dynamicSmemBytes = CskCfg<BN, STAGES>::SMEM_BYTES;
+  cfg.gridDim = dim3(S * 64); cfg.blockDim = dim3(kCskThreads); cfg.dynamicSmemBytes = CskCfg<BN, STAGES, NBUF>::SMEM_BYTES;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_csk_kernel<BN, STAGES>, &cfg) != cudaSuccess || n <= 0) {
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_csk_kernel<BN, STAGES, NBUF>, &cfg) != cudaSuccess || n <= 0) {
     (void)cudaGetLastError();
     n = (2 * num_sms()) / S * 3 / 4;                 // conservative fallback
     if (n < 1) n = 1;
   }
+  // The cluster occupancy query counts ONE CTA per SM on this driver even when two fit (shared memory, registers and the plain
+  // per-SM occupancy query all allow 2): scale by the per-SM block occupancy, capped at 2 (the launch bound).
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_csk_kernel<BN, STAGES, NBUF>, kCskThreads, CskCfg<BN, STAGES, NBUF>::SMEM_BYTES) != cudaSuccess) { (void)cudaGetLastError(); per_sm = 1; }
+  if (per_sm > 2) per_sm = 2;
+  // Measured on B200 (profiles/r2_csk_sweep_*.json): both occupancy queries answer 1 block per SM -- also for gemm.cu's swap-AB
+  // kernel, which demonstrably runs two -- while launching twice as many clusters makes every decode GEMM 10-30 % faster: the
+  // kernel is sized for 2 CTAs per SM (launch bound, <= 101 KB of shared memory), so that is what the launch assumes.
+  int mult = 2;
+  if (const char* e = getenv("VCLA_CSK_OCC")) { const int v = atoi(e); if (v >= 1 && v <= 2) mult = v; }
+  if (getenv("VCLA_DEBUG")) fprintf(stderr, "[vcla] gemm_csk<%d,%d> S=%d: cluster query %d, blocks/SM %d, using x%d\n", BN, STAGES, S, n, per_sm, mult);
+  n *= mult;
   cache[S] = n;
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBUF>
 static int csk_launch(const CskCall& c, CskParams p, cudaStream_t st) {
   CUtensorMap tw, tx;
   if (csk_tmap(&tw, c.W, c.M, c.K, c.K, kCskBlockM)) return -1;
   if (csk_tmap(&tx, c.X, c.B, c.K, c.K, BN)) return -1;
-  int ncl = csk_max_clusters<BN, STAGES>(p.splits);
+  int ncl = csk_max_clusters<BN, STAGES, NBUF>(p.splits);
   if (ncl > p.m_tiles) ncl = p.m_tiles;
   p.n_clusters = ncl;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(ncl * p.splits); cfg.blockDim = dim3(kCskThreads); cfg.dynamicSmemBytes = CskCfg<BN, STAGES>::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(ncl * p.splits); cfg.blockDim = dim3(kCskThreads); cfg.dynamicSmemBytes = CskCfg<BN, STAGES, NBUF>::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int na = 0;
   attr[na].id = cudaLaunchAttributeClusterDimension;
@@ -385,14 +426,30 @@ static int csk_launch(const CskCall& c, CskParams p, cudaStream_t st) {
   ++na;
   if (pdl_enabled()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
   cfg.attrs = attr; cfg.numAttrs = na;
-  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_csk_kernel<BN, STAGES>, tw, tx, p));
+  VCLA_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_csk_kernel<BN, STAGES, NBUF>, tw, tx, p));
   return 0;
+}
+
+// Reduce buffering, measured on B200 (profiles/r2_bench_ab.jsonl): batch <= 16 (16-column tile): double-buffered reduce + 4 TMA stages
+// (2.880 vs 2.899 ms/token at batch 8); batch 17..32 (32-column tile): ONE buffer + 'consumed' barrier, which frees the shared memory
+// for a 4th TMA stage (4.279 vs 4.375 ms/token at batch 32).  VCLA_CSK_NBUF = 1 / 2 forces one scheme for both.
+static int csk_nbuf_env() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VCLA_CSK_NBUF"); v = e != nullptr ? atoi(e) : 0; }
+  return v;
+}
+static bool csk_double_buffered(int B) {
+  const int f = csk_nbuf_env();
+  if (f == 1) return false;
+  if (f == 2) return true;
+  return B <= 16;
 }
 
 int gemm_csk_clusters(int B, int splits) {
   if (csk_init()) return -1;
   if (splits < 1 || splits > kCskMaxSplits) return -1;
-  return B <= 16 ? csk_max_clusters<16, 5>(splits) : csk_max_clusters<32, 3>(splits);
+  if (csk_double_buffered(B)) return B <= 16 ? csk_max_clusters<16, 4, 2>(splits) : csk_max_clusters<32, 3, 2>(splits);
+  return B <= 16 ? csk_max_clusters<16, 5, 1>(splits) : csk_max_clusters<32, 4, 1>(splits);
 }
 
 int gemm_csk(const CskCall& c, cudaStream_t st) {
@@ -411,6 +468,7 @@ int gemm_csk(const CskCall& c, cudaStream_t st) {
   p.mode = c.mode; p.out = c.out; p.ldo = c.ldo; p.resid = c.resid; p.norm_w = c.norm_w; p.xw = c.xw; p.ssq_out = c.ssq_out; p.h = c.h;
   p.ssq_in = c.ssq_in; p.ssq_slots = c.ssq_slots; p.inv_dim = c.inv_dim; p.eps = c.eps;
   p.policy_w = kEvictFirst; p.policy_x = kEvictLast;
+  { static int fence = -1; if (fence < 0) { const char* e = getenv("VCLA_CSK_FENCE"); fence = e ? atoi(e) : 0; } p.cluster_fence = fence; }
   if (c.mode == CSK_OUT_F32 && (!c.out || c.ldo < c.M)) { set_error("gemm_csk: OUT_F32 needs out / ldo"); return -1; }
   if (c.mode == CSK_RESID && (!c.resid || !c.norm_w || !c.xw || !c.ssq_out)) { set_error("gemm_csk: RESID needs resid / norm_w / xw / ssq_out"); return -1; }
   if (c.mode == CSK_SWIGLU && (!c.h || (c.M % 64) != 0)) { set_error("gemm_csk: SWIGLU needs h and rows %% 64 == 0"); return -1; }
@@ -418,8 +476,8 @@ int gemm_csk(const CskCall& c, cudaStream_t st) {
     const int cols_per = (c.B + p.splits - 1) / p.splits, bn = c.B <= 16 ? 16 : 32;
     if (cols_per * p.splits > bn + 4) { set_error("gemm_csk: %d splits of batch %d need %d reduce columns (max %d)", p.splits, c.B, cols_per * p.splits, bn + 4); return -1; }
   }
-  if (c.B <= 16) return csk_launch<16, 5>(c, p, st);
-  return csk_launch<32, 3>(c, p, st);
+  if (csk_double_buffered(c.B)) return c.B <= 16 ? csk_launch<16, 4, 2>(c, p, st) : csk_launch<32, 3, 2>(c, p, st);
+  return c.B <= 16 ? csk_launch<16, 5, 1>(c, p, st) : csk_launch<32, 4, 1>(c, p, st);
 }
 
 }  // namespace vcla

@@ -136,6 +136,8 @@ int gemm_csk(const CskCall& c, cudaStream_t st);
 int gemm_csk_clusters(int B, int splits);   // clusters of `splits` CTAs that can be co-resident (occupancy query, cached)
 int trace_set_gemm(void* buf, unsigned long long cap);
 int trace_set_attention(void* buf, unsigned long long cap);
+int trace_set_gemm_decode(void* buf, unsigned long long cap);
+int trace_set_sampler(void* buf, unsigned long long cap);
 int trace_set_elementwise(void* buf, unsigned long long cap);
 
 // ------------------------------------------------------------------------------------------

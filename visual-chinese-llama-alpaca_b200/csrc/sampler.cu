@@ -235,4 +235,6 @@ int sampler_init() {
   return 0;
 }
 
+VCLA_DEFINE_TRACE_SETTER(trace_set_sampler)
+
 }  // namespace vcla
