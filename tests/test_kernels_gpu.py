@@ -135,9 +135,19 @@ def _attn_ref(q, k, v, scale, causal):
     return (torch.softmax(s, -1) @ vf).transpose(1, 2)
 
 
+@pytest.fixture(params=[0, 1], ids=["mma_sync", "tcgen05"])
+def attn_impl(request, lib):
+    """Both prefill attention kernels behind the same entry point: the mma.sync one (csrc/attention.cu) and the tcgen05 one
+    (csrc/attention_tc.cu: QK^T and PV as UMMA, S / O in TMEM, TMA operands)."""
+    lib.vcla_set_attention_tc(request.param)
+    yield request.param
+    lib.vcla_set_attention_tc(int(__import__("os").environ.get("VCLA_ATTN_TC", "1")))
+
+
 @pytest.mark.parametrize("B,H,S,HD,causal", [(2, 16, 257, 64, 0), (3, 2, 17, 64, 0), (2, 32, 96, 128, 1), (1, 4, 200, 128, 1),
-                                              (2, 2, 64, 128, 1), (1, 2, 1, 128, 1)])
-def test_attention_self(lib, B, H, S, HD, causal):
+                                              (2, 2, 64, 128, 1), (1, 2, 1, 128, 1), (2, 4, 128, 128, 1), (1, 2, 1088, 128, 1),
+                                              (2, 3, 300, 64, 1), (1, 2, 640, 64, 0)])
+def test_attention_self(lib, attn_impl, B, H, S, HD, causal):
     D = H * HD
     qkv = _rand((B * S, 3 * D), 1.0, 20)
     out = torch.empty((B * S, D), dtype=torch.bfloat16, device="cuda")
@@ -150,7 +160,7 @@ def test_attention_self(lib, B, H, S, HD, causal):
     assert (out.float() - ref).abs().max().item() <= 2e-2
 
 
-def test_attention_two_segments(lib):
+def test_attention_two_segments(lib, attn_impl):
     """Resampler layout: 64 queries attend over [their own 64 rows ; 257 image rows] (ref resampler :315)."""
     B, H, HD, Q, NI, L = 2, 16, 64, 64, 257, 3
     D = H * HD

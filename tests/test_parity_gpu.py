@@ -333,6 +333,32 @@ def test_lora_fold_at_load(tmp_path):
     assert _rel_err(got, ref) <= LOGIT_TOL
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["mma_sync", "tcgen05"])
+def test_prefill_attention_kernels_end_to_end(golden_dir, impl):
+    """Both prefill attention kernels through the whole path: ViT (257 tokens, hd 64), Resampler (two KV segments), LLaMA causal
+    prefill over several KV tiles, and left padding (kv_start) against the reference's padded golden."""
+    from visualcla import _native as N
+    lib = N.load()
+    lib.vcla_set_attention_tc(impl)
+    try:
+        cfg = O.PathConfig(v_layers=2, r_layers=2, t_hidden=1024, t_heads=8, t_ffn=2752, t_layers=3, t_vocab=5003)
+        m, err, nbad, ndec, ntot, _, _ = _run_vs_oracle(cfg, 5, 3, 300, 6, 512)
+        assert err <= LOGIT_TOL, f"teacher-forced logits rel err {err:.3e}"
+        assert nbad == 0
+        g, gcfg = _load_golden(golden_dir, "tiny_padded")
+        mp = _model(gcfg, int(g["seed"]), 4, 96)
+        s0, s1, s2, s3 = O.special_ids(gcfg)
+        mp.image_at_head = False
+        mp.tokenizer = types.SimpleNamespace(img_start_token_id=s0, img_end_token_id=s1, img_token_id=s3)
+        px, ids, mask = (torch.from_numpy(g[k]).cuda() for k in ("pixel_values", "input_ids", "attention_mask"))
+        fwd = mp.forward(input_ids=ids, pixel_values=px, attention_mask=mask).logits.cpu()
+        ref = torch.from_numpy(g["forward_logits"])
+        for b, p in enumerate(g["pads"].tolist()):
+            assert _rel_err(fwd[b, p:], ref[b, p:]) <= LOGIT_TOL
+    finally:
+        lib.vcla_set_attention_tc(int(os.environ.get("VCLA_ATTN_TC", "1")))
+
+
 @pytest.mark.parametrize("B", [1, 5, 16, 17, 32])
 def test_cluster_splitk_decode_over_batch_sizes(B):
     """Cluster split-K decode GEMMs: every batch tile (16 / 32 columns), uneven column ownership (batch not a multiple of the

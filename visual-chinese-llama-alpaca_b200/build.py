@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libvcla.so")
-SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "engine.cu", "preprocess.cu", "sampler.cu", "gemm_decode.cu"]
+SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "engine.cu", "preprocess.cu", "sampler.cu", "gemm_decode.cu", "attention_tc.cu"]
 HEADERS = ["common.cuh", "kernels.h", "preprocess_core.h", os.path.join("..", "..", "include", "vcla.h")]
 
 

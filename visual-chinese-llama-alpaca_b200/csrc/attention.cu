@@ -194,7 +194,18 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   }
 }
 
+static int g_attn_tc = -1;
+void attention_set_tc(int on) { g_attn_tc = on ? 1 : 0; }
 int attention_prefill(const AttnCall& c, cudaStream_t st) {
+  if (g_attn_tc < 0) { const char* e = getenv("VCLA_ATTN_TC"); g_attn_tc = (e != nullptr) ? (atoi(e) != 0) : 0; }
+  // the tcgen05 kernel needs TMA-describable operands (16 B aligned, 16 B-multiple pitches) and one KV segment when causal
+  const bool tma_ok = (c.q_stride % 8) == 0 && (c.kv0_stride % 8) == 0 && (c.n1 == 0 || (c.kv1_stride % 8) == 0) && (c.o_stride % 8) == 0 &&
+                      !(c.causal && c.n1 > 0);
+  if (g_attn_tc == 1 && tma_ok) return attention_prefill_tc(c, st);
+  return attention_prefill_mma(c, st);
+}
+
+int attention_prefill_mma(const AttnCall& c, cudaStream_t st) {
   if (c.HD != 64 && c.HD != 128) { set_error("attention_prefill: head dim %d unsupported (64/128)", c.HD); return -1; }
   if ((c.q_stride % 8) || (c.kv0_stride % 8) || (c.n1 > 0 && (c.kv1_stride % 8)) || (c.o_stride % 2)) {
     set_error("attention_prefill: strides must keep 16 B alignment");

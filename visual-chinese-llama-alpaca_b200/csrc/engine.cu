@@ -504,7 +504,7 @@ void vcla_destroy(vcla_ctx* c) {
   if (c->dp_fork) cudaEventDestroy(c->dp_fork);
   if (c->dp_join) cudaEventDestroy(c->dp_join);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
-  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_gemm_decode(nullptr, 0); trace_set_sampler(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); }
+  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_attention_tc(nullptr, 0); trace_set_gemm_decode(nullptr, 0); trace_set_sampler(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); }
   delete c;
 }
 
@@ -1308,13 +1308,13 @@ int vcla_read_history(vcla_ctx* c, int32_t* dst_dev, int B, int n_steps, vcla_st
 int vcla_trace_enable(vcla_ctx* c, int max_events) {
   // installs (max_events > 0) or removes (0) the timeline buffer every kernel's CTA 0 appends to
   VCLA_CUDA_OK(cudaDeviceSynchronize());
-  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_gemm_decode(nullptr, 0); trace_set_sampler(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); c->trace_buf = nullptr; c->trace_cap = 0; }
+  if (c->trace_buf) { trace_set_gemm(nullptr, 0); trace_set_attention_tc(nullptr, 0); trace_set_gemm_decode(nullptr, 0); trace_set_sampler(nullptr, 0); trace_set_attention(nullptr, 0); trace_set_elementwise(nullptr, 0); cudaFree(c->trace_buf); c->trace_buf = nullptr; c->trace_cap = 0; }
   if (max_events <= 0) return 0;
   const size_t bytes = 8 + (size_t)max_events * 32;
   VCLA_CUDA_OK(cudaMalloc(&c->trace_buf, bytes));
   VCLA_CUDA_OK(cudaMemset(c->trace_buf, 0, bytes));
   c->trace_cap = (unsigned long long)max_events;
-  if (trace_set_gemm(c->trace_buf, c->trace_cap) || trace_set_gemm_decode(c->trace_buf, c->trace_cap) || trace_set_sampler(c->trace_buf, c->trace_cap) || trace_set_attention(c->trace_buf, c->trace_cap) || trace_set_elementwise(c->trace_buf, c->trace_cap)) {
+  if (trace_set_gemm(c->trace_buf, c->trace_cap) || trace_set_attention_tc(c->trace_buf, c->trace_cap) || trace_set_gemm_decode(c->trace_buf, c->trace_cap) || trace_set_sampler(c->trace_buf, c->trace_cap) || trace_set_attention(c->trace_buf, c->trace_cap) || trace_set_elementwise(c->trace_buf, c->trace_cap)) {
     set_error("vcla_trace_enable: cudaMemcpyToSymbol failed");
     return -1;
   }
@@ -1372,6 +1372,7 @@ int vcla_debug_get_csk_splits(vcla_ctx* c, int B, int* out5) {
 }
 int vcla_op_gemm_csk_clusters(int B, int splits) { return gemm_csk_clusters(B, splits); }
 void vcla_set_gemm_two_cta(int on) { gemm_set_two_cta(on); }
+void vcla_set_attention_tc(int on) { attention_set_tc(on); }
 int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1, const void* v1,
                       int kv1_stride, int n1, void* out, int o_stride, int B, int H, int Sq, int HD, float scale, int causal, vcla_stream stream) {
   AttnCall a; a.q = (const bf16*)q; a.q_stride = q_stride; a.k0 = (const bf16*)k0; a.v0 = (const bf16*)v0; a.kv0_stride = kv0_stride; a.n0 = n0;

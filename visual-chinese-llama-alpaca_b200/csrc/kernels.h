@@ -153,7 +153,11 @@ struct AttnCall {
   int causal = 0;
   const int32_t* kv_start = nullptr;   // [B] first visible kv index per sequence (left padding); null: 0
 };
-int attention_prefill(const AttnCall& c, cudaStream_t st);
+int attention_prefill(const AttnCall& c, cudaStream_t st);      // dispatches to the tcgen05 kernel (attention_tc.cu) unless switched off
+int attention_prefill_tc(const AttnCall& c, cudaStream_t st);   // tcgen05: QK^T and PV as UMMA, S / O in TMEM, Q / K / V by TMA
+int attention_prefill_mma(const AttnCall& c, cudaStream_t st);  // mma.sync m16n8k16 fallback (attention.cu)
+void attention_set_tc(int on);                                   // 1: tcgen05 kernel, 0: mma.sync kernel (VCLA_ATTN_TC)
+int trace_set_attention_tc(void* buf, unsigned long long cap);
 
 struct DecodeAttnCall {
   const float* qkv_partial = nullptr;  // [splits][ws_rows][3*T] fp32 split-K partials of the fused QKV projection
