@@ -316,6 +316,25 @@ def run_config(args, world, rank, Bl, T, n_new, steps, warmup, with_e2e, with_tr
         assert torch.equal(out_e2e, out.cpu()), "e2e and device-resident runs must produce the same tokens"
         res["e2e"] = {"value": B * steps / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(px_h.numel() * 2 + ids_h.numel() * 8),
                       "d2h_bytes_per_step": int(B * n_new * 8), "ms_per_step": ms_e2e / steps}
+    if with_trace and world == 1:
+        # chat()'s real default is SAMPLING (ref modeling_utils.py:36-47): the same workload through VisualCLAModel.generate with the
+        # reference's DEFAULT_GENERATION_CONFIG -- repetition penalty, no-repeat-ngram, temperature, top-k, top-p and the draw run in
+        # one fused kernel per step inside the decode graphs (csrc/sampler.cu)
+        try:
+            import copy
+            from visualcla.modeling_utils import DEFAULT_GENERATION_CONFIG
+            gcs = copy.deepcopy(DEFAULT_GENERATION_CONFIG)
+            gcs.max_new_tokens, gcs.eos_token_id, gcs.pad_token_id = n_new, None, 0
+
+            def step_sample():
+                return model.generate(input_ids=ids_d, pixel_values=px_d, generation_config=gcs)
+            step_sample()
+            ms_s, out_s = timed(step_sample, 2)
+            res["sampling"] = {"value": B * 2 / (ms_s / 1000.0), "unit": UNIT, "ms_per_step": ms_s / 2, "steps": 2,
+                               "config": "DEFAULT_GENERATION_CONFIG (do_sample, temperature 0.5, top_k 40, top_p 0.9, repetition_penalty 1.1, no_repeat_ngram_size 15), "
+                                         "device-side fused sampler inside the decode CUDA graphs", "shape": list(out_s.shape)}
+        except Exception as e:  # noqa: BLE001
+            res["sampling"] = {"error": repr(e)}
     if with_trace and rank == 0:
         # the caches now hold S + n_new - 1 tokens: the traced step runs at the END-of-generation context
         tok = eng.token_buffer(Bl)
@@ -379,6 +398,11 @@ def run_native(args):
             "e2e": main["e2e"], "gpu_launches": int(main["launches"]), "clocks": main["clocks"]}
     if "phases" in main:
         line["phases"] = main["phases"]
+    if "sampling" in main:
+        line["sampling"] = main["sampling"]
+    line["config"]["schedule"] = ("prefill: 5 kernels/layer (deferred RMSNorm + RoPE/KV-append + SwiGLU + residual epilogues in the tcgen05 GEMM, CTA-pair 256x256 "
+                                  "tiles, tcgen05 flash attention); decode: 5 kernels/layer (cluster split-K GEMMs with DSMEM reduce and fused consumers), "
+                                  "CUDA graphs of 16 steps")
     if rank == 0:
         # ---- roofline of the dominant kernel, IN SITU: the fused gate/up swap-AB tcgen05 GEMM (180.4 MB of weights per launch, the
         #      largest share of a decode step), timed inside a graph-replayed decode step; the isolated micro-benchmark (32 launches

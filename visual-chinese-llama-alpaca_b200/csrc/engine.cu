@@ -456,6 +456,7 @@ int vcla_create(const vcla_config* cfg, vcla_ctx** out) {
   if (c->fused_decode) c->decode_schedule = 1;
   c->fused_decode = c->decode_schedule == 1;
   c->kv_splits = g.max_seq >= 1536 ? 4 : (g.max_seq >= 768 ? 2 : 1);   // context-driven minimum; raised per call for small batches
+  if (const char* e = getenv("VCLA_KV_SPLITS")) { const int v = atoi(e); if (v >= 1 && v <= 8) c->kv_splits = v; }   // tuning override
 
   if (gemm_init()) { delete c; return -1; }
   // sizing passes
