@@ -40,12 +40,17 @@ struct AttnTcCfg {
   static constexpr int K_BYTES = KB * kAtBKV * 128;
   static constexpr int V_BYTES = KB * kAtBKV * 128;          // [KB (head-dim halves)][128 kv rows][128 B]
   static constexpr int P_BYTES = 2 * kAtBQ * 128;            // [2 kv k-blocks][128 rows][128 B]
+  // hd 128: one CTA per SM (192 KB of shared memory), so the CTA overlaps its own phases: 2 K/V stages, 2 score buffers in TMEM.
+  // hd 64: TWO CTAs per SM (80 KB, 256 TMEM columns each) overlap each other instead: 1 K/V stage, 1 score buffer.
+  static constexpr int NSTAGE = HD == 64 ? 1 : 2;
+  static constexpr int NSBUF = HD == 64 ? 1 : 2;
+  static constexpr int CTAS_PER_SM = HD == 64 ? 2 : 1;
   static constexpr int KV_OFF = Q_BYTES;
-  static constexpr int P_OFF = KV_OFF + 2 * (K_BYTES + V_BYTES);
+  static constexpr int P_OFF = KV_OFF + NSTAGE * (K_BYTES + V_BYTES);
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
-  static constexpr int TMEM_COLS = 512;                      // S: 2 x 128 columns, O: HD columns
-  static constexpr uint32_t O_COL = 256;
+  static constexpr int TMEM_COLS = HD == 64 ? 256 : 512;     // S: NSBUF x 128 columns, then O: HD columns
+  static constexpr uint32_t O_COL = NSBUF * 128;
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -74,7 +79,7 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 constexpr uint32_t kIdescBMajorMN = 1u << 16;
 
 template <int HD>
-__global__ void __launch_bounds__(kAtThreads, 1)
+__global__ void __launch_bounds__(kAtThreads, AttnTcCfg<HD>::CTAS_PER_SM)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                        const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1, const AttnTcParams p) {
   using C = AttnTcCfg<HD>;
@@ -128,8 +133,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
       for (int kb = 0; kb < C::KB; ++kb) tma_load_2d(base + kb * kAtBQ * 128, &tmQ, h * HD + kb * 64, b * p.Sq + q0, q_full, kEvictNormal);
       for (int i = 0; i < n_tiles; ++i) {
-        const int j = jt0 + i, stage = i & 1;
-        mbar_wait(kv_empty(stage), (((uint32_t)i >> 1) & 1u) ^ 1u);
+        const int j = jt0 + i, stage = i % C::NSTAGE;
+        mbar_wait(kv_empty(stage), (((uint32_t)(i / C::NSTAGE)) & 1u) ^ 1u);
         mbar_arrive_expect_tx(kv_full(stage), C::K_BYTES + C::V_BYTES);
         const uint32_t sk = base + C::KV_OFF + stage * (C::K_BYTES + C::V_BYTES), sv = sk + C::K_BYTES;
         const bool seg1 = j >= nt0;
@@ -148,27 +153,27 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_s = make_idesc_bf16(kAtBQ, kAtBKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(kAtBQ, HD) | kIdescBMajorMN;
-      auto issue_s = [&](int i) {                              // S[i & 1] = Q K_i^T
-        const int stage = i & 1;
-        mbar_wait(kv_full(stage), ((uint32_t)i >> 1) & 1u);
+      auto issue_s = [&](int i) {                              // S[i % NSBUF] = Q K_i^T
+        const int stage = i % C::NSTAGE, sbuf = i % C::NSBUF;
+        mbar_wait(kv_full(stage), ((uint32_t)(i / C::NSTAGE)) & 1u);
         tc_fence_after();
         const uint32_t sk = base + C::KV_OFF + stage * (C::K_BYTES + C::V_BYTES);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(stage * kAtBKV);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(sbuf * kAtBKV);
 #pragma unroll
         for (int kb = 0; kb < C::KB; ++kb) {
           const uint64_t adesc = make_desc_sw128(base + kb * kAtBQ * 128), bdesc = make_desc_sw128(sk + kb * kAtBKV * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc_s, (kb > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(s_full(stage));
+        umma_commit(s_full(sbuf));
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int i = 0; i < n_tiles; ++i) {
-        if (i + 1 < n_tiles) issue_s(i + 1);                   // overlaps the softmax of tile i
+        if (C::NSBUF == 2 && i + 1 < n_tiles) issue_s(i + 1);  // two score buffers: overlaps the softmax of tile i
         mbar_wait(p_ready, (uint32_t)i & 1u);
         tc_fence_after();
-        const int stage = i & 1;
+        const int stage = i % C::NSTAGE;
         const uint32_t sv = base + C::KV_OFF + stage * (C::K_BYTES + C::V_BYTES) + C::K_BYTES;
         const uint32_t sp = base + C::P_OFF;
         const uint32_t o_tmem = tmem_base + C::O_COL;
@@ -180,6 +185,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         umma_commit(kv_empty(stage));                          // K/V stage (and P) reusable
         umma_commit(o_done);
+        // one score buffer / one K/V stage: the next tile's K arrives only after this commit frees the stage; the scores of
+        // tile i were consumed before p_ready(i).  (The other CTA on the SM keeps the tensor core busy meanwhile.)
+        if (C::NSBUF == 1 && i + 1 < n_tiles) issue_s(i + 1);
       }
     }
     __syncwarp();
@@ -192,14 +200,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* p_row = base_ptr + C::P_OFF + (size_t)r * 128;     // + kv k-block * 16 KB; 16 B chunk c sits at (c ^ (r & 7)) * 16
     for (int i = 0; i < n_tiles; ++i) {
-      const int j = jt0 + i, buf = i & 1;
+      const int j = jt0 + i, buf = i % C::NSBUF;
       const bool seg1 = j >= nt0;
       const int kbase = seg1 ? p.n0 + (j - nt0) * kAtBKV : j * kAtBKV;       // global key index of the tile's first row
       const int kvalid = seg1 ? p.n1 - (j - nt0) * kAtBKV : p.n0 - j * kAtBKV; // keys of this tile that exist in the segment
       int hi = min(kvalid, kAtBKV);
       if (p.causal) hi = min(hi, qi + off - kbase + 1);
       const int lo = max(kv0 - kbase, 0);
-      mbar_wait(s_full(buf), ((uint32_t)i >> 1) & 1u);
+      mbar_wait(s_full(buf), ((uint32_t)(i / C::NSBUF)) & 1u);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + (uint32_t)(buf * kAtBKV);
       // pass 1: row maximum of the visible scores

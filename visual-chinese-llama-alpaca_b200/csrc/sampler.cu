@@ -64,6 +64,7 @@ dec_sample_kernel(const float* __restrict__ logits, int ld, int V, int B, const 
   float* s_sval = reinterpret_cast<float*>(s_idx + kSampMaxKeep);
   int* s_sidx = reinterpret_cast<int*>(s_sval + kSampMaxKeep);
   __shared__ int s_cnt, s_n, s_choice, s_keep;
+  __shared__ unsigned int s_thr;
   __shared__ float s_bv[32];
   __shared__ int s_bi[32];
 
@@ -78,7 +79,7 @@ dec_sample_kernel(const float* __restrict__ logits, int ld, int V, int B, const 
 
   for (int v = tid; v < V; v += kSampThreads) s_row[v] = logits[(size_t)b * ld + v];
   for (int i = tid; i < vpad / 32; i += kSampThreads) s_seen[i] = 0u;
-  if (tid == 0) { s_n = 0; s_choice = 0; s_keep = 0; }
+  if (tid == 0) { s_n = 0; s_choice = 0; s_keep = 0; s_thr = 0xFFFFFFFFu; }
   __syncthreads();
 
   // ---- repetition penalty: once per distinct token of the history
@@ -140,14 +141,54 @@ dec_sample_kernel(const float* __restrict__ logits, int ld, int V, int B, const 
       for (int v = tid; v < V; v += kSampThreads) s_row[v] = __fdiv_rn(s_row[v], p.temperature);
       __syncthreads();
     }
-    // ---- top-k threshold: the k-th largest key, built bit by bit (largest T with count(key >= T) >= k)
+    // ---- top-k threshold = the k-th largest key.  Two levels instead of 32 counting passes over the whole row:
+    //  (1) T1 = the k-th largest of the 1024 per-thread maxima (bit search with __syncthreads_count: one barrier per bit).  At least
+    //      k elements are >= T1, so the k-th largest element of the row is >= T1: every top-k element survives the pre-filter.
+    //  (2) the (few) elements >= T1 are collected and the exact k-th largest is found among them.
+    // If the pre-filter keeps more than the candidate buffer holds (a row full of ties), the exact bit search over the row runs.
     const int k = p.top_k < V ? p.top_k : V;
+    uint32_t my_max = 0u;
+    for (int v = tid; v < V; v += kSampThreads) { const uint32_t key = order_key(s_row[v]); my_max = key > my_max ? key : my_max; }
     uint32_t T = 0u;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = T | (1u << bit);
-      int c = 0;
-      for (int v = tid; v < V; v += kSampThreads) c += order_key(s_row[v]) >= cand;
-      if (block_count(c, &s_cnt) >= k) T = cand;
+    if (k <= kSampThreads) {
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        if (__syncthreads_count(my_max >= cand) >= k) T = cand;
+      }
+      int c1 = 0;
+      for (int v = tid; v < V; v += kSampThreads) c1 += order_key(s_row[v]) >= T;
+      const int n1 = block_count(c1, &s_cnt);
+      if (n1 <= kSampMaxKeep) {
+        // exact k-th largest among the n1 pre-filtered elements (rank by counting)
+        for (int v = tid; v < V; v += kSampThreads) {
+          const float x = s_row[v];
+          if (order_key(x) >= T) { const int pos = atomicAdd(&s_n, 1); s_val[pos] = x; s_idx[pos] = v; }
+        }
+        __syncthreads();
+        if (tid < n1) {
+          const uint32_t kx = order_key(s_val[tid]);
+          int greater = 0;
+          for (int j = 0; j < n1; ++j) greater += order_key(s_val[j]) > kx;
+          // the k-th largest value is the smallest key that still has fewer than k strictly greater elements
+          if (greater < k) atomicMin(&s_thr, kx);
+        }
+        __syncthreads();
+        T = s_thr;
+        __syncthreads();
+        if (tid == 0) { s_n = 0; }
+        __syncthreads();
+      } else {
+        T = 0u;
+      }
+    }
+    if (T == 0u) {
+      // exact bit search over the whole row: largest T with count(key >= T) >= k
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        int c = 0;
+        for (int v = tid; v < V; v += kSampThreads) c += order_key(s_row[v]) >= cand;
+        if (block_count(c, &s_cnt) >= k) T = cand;
+      }
     }
     // ---- candidates (k plus ties), sorted by (value desc, index asc)
     for (int v = tid; v < V; v += kSampThreads) {
