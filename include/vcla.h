@@ -228,8 +228,9 @@ int vcla_debug_set_csk_splits(vcla_ctx* ctx, int B, int qkv, int o, int gate_up,
 int vcla_debug_get_csk_splits(vcla_ctx* ctx, int B, int* out5);
 /* CTA-pair (tcgen05 cta_group::2, 256 x 256) tiles for the 256-wide prefill GEMMs: on by default; 0 selects the single-CTA 128 x 256 tile */
 void vcla_set_gemm_two_cta(int on);
-/* prefill attention kernel: 1 = tcgen05 flash attention (QK^T / PV as UMMA, S and O in TMEM, TMA operands), 0 = the mma.sync kernel */
-void vcla_set_attention_tc(int on);
+/* prefill attention kernel: 0 = the mma.sync kernel everywhere, 1 (default) = tcgen05 flash attention (QK^T / PV as UMMA, S and O in TMEM,
+ * TMA operands) at head dim 128 (LLaMA prefill) and mma.sync at head dim 64 (ViT / Resampler), 2 = tcgen05 everywhere */
+void vcla_set_attention_tc(int mode);
 int vcla_op_attention(const void* q, int q_stride, const void* k0, const void* v0, int kv0_stride, int n0, const void* k1,
                       const void* v1, int kv1_stride, int n1, void* out, int o_stride, int B, int H, int Sq, int HD, float scale,
                       int causal, vcla_stream stream);

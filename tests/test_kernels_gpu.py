@@ -135,7 +135,7 @@ def _attn_ref(q, k, v, scale, causal):
     return (torch.softmax(s, -1) @ vf).transpose(1, 2)
 
 
-@pytest.fixture(params=[0, 1], ids=["mma_sync", "tcgen05"])
+@pytest.fixture(params=[0, 2], ids=["mma_sync", "tcgen05"])
 def attn_impl(request, lib):
     """Both prefill attention kernels behind the same entry point: the mma.sync one (csrc/attention.cu) and the tcgen05 one
     (csrc/attention_tc.cu: QK^T and PV as UMMA, S / O in TMEM, TMA operands)."""

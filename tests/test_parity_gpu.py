@@ -335,7 +335,7 @@ def test_lora_fold_at_load(tmp_path):
     assert _rel_err(got, ref) <= LOGIT_TOL
 
 
-@pytest.mark.parametrize("impl", [0, 1], ids=["mma_sync", "tcgen05"])
+@pytest.mark.parametrize("impl", [0, 2], ids=["mma_sync", "tcgen05"])
 def test_prefill_attention_kernels_end_to_end(golden_dir, impl):
     """Both prefill attention kernels through the whole path: ViT (257 tokens, hd 64), Resampler (two KV segments), LLaMA causal
     prefill over several KV tiles, and left padding (kv_start) against the reference's padded golden."""

@@ -194,16 +194,18 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnCall c) {
   }
 }
 
+// 0 = mma.sync kernel for everything, 1 (default) = tcgen05 kernel where it is the faster one on B200 (head dim 128: LLaMA prefill),
+// 2 = tcgen05 kernel for everything it can describe (tests).  Measured under ncu (profiles/r2_ncu_kernels.json, attn reports): the
+// ViT's 257 tokens at head dim 64 waste a third of the 128-row UMMA tiles and stay on mma.sync (25.8 vs 42 us per launch at batch 8).
 static int g_attn_tc = -1;
-void attention_set_tc(int on) { g_attn_tc = on ? 1 : 0; }
+void attention_set_tc(int mode) { g_attn_tc = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 int attention_prefill(const AttnCall& c, cudaStream_t st) {
-  // default: the tcgen05 kernel (parity-tested against the same oracle; measured on B200 within noise of the mma.sync kernel at the
-  // benchmark shapes: profiles/r2_bench_ab.jsonl); VCLA_ATTN_TC=0 selects the mma.sync kernel
-  if (g_attn_tc < 0) { const char* e = getenv("VCLA_ATTN_TC"); g_attn_tc = (e != nullptr) ? (atoi(e) != 0) : 1; }
+  if (g_attn_tc < 0) { const char* e = getenv("VCLA_ATTN_TC"); g_attn_tc = (e != nullptr) ? atoi(e) : 1; if (g_attn_tc < 0 || g_attn_tc > 2) g_attn_tc = 1; }
   // the tcgen05 kernel needs TMA-describable operands (16 B aligned, 16 B-multiple pitches) and one KV segment when causal
   const bool tma_ok = (c.q_stride % 8) == 0 && (c.kv0_stride % 8) == 0 && (c.n1 == 0 || (c.kv1_stride % 8) == 0) && (c.o_stride % 8) == 0 &&
                       !(c.causal && c.n1 > 0);
-  if (g_attn_tc == 1 && tma_ok) return attention_prefill_tc(c, st);
+  const bool want_tc = g_attn_tc == 2 || (g_attn_tc == 1 && c.HD == 128);
+  if (want_tc && tma_ok) return attention_prefill_tc(c, st);
   return attention_prefill_mma(c, st);
 }
 

@@ -3,14 +3,14 @@
 //
 // One CTA per (128 query rows, head, sequence).  Both contractions run on the 5th-generation tensor cores:
 //   S = Q K^T   UMMA 128 x 128 x HD   A = Q tile, B = K tile, both K-major [rows][64-element k-blocks] staged by TMA (128 B swizzle);
-//               fp32 scores in TMEM, double buffered so that S of tile j+1 is computed while the softmax of tile j runs
+//               fp32 scores in TMEM
 //   O += P V    UMMA 128 x HD x 128   A = P (bf16 probabilities written by the softmax warps into shared memory in the same K-major
 //               swizzled layout), B = V tile exactly as TMA delivers it ([kv rows][64 head dims] = an MN-major operand: the
 //               instruction descriptor's b_major bit + a matrix descriptor with SBO = 8 rows, LBO = the next 64 head dims)
 // O accumulates in TMEM; the online-softmax rescale (O *= exp2(m_old - m_new)) is a tcgen05.ld / multiply / tcgen05.st of the row
 // by the thread that owns it, between the PV MMAs of consecutive tiles.
 //
-// Warps: 0 = TMA producer (Q once, then K/V tiles through a 2-stage ring), 1 = MMA issuer + TMEM owner, 2..5 = softmax / rescale /
+// Warps: 0 = TMA producer (Q once, then the K/V tiles), 1 = MMA issuer + TMEM owner, 2..5 = softmax / rescale /
 // epilogue (thread t owns query row t = TMEM lane t).  Masks: keys past a segment's end, causal (key <= query + Sk - Sq), left padding
 // (kv_start).  Fully masked rows produce zeros, like the mma.sync kernel this replaces (csrc/attention.cu, kept as the fallback).
 #include "common.cuh"
@@ -40,16 +40,20 @@ struct AttnTcCfg {
   static constexpr int K_BYTES = KB * kAtBKV * 128;
   static constexpr int V_BYTES = KB * kAtBKV * 128;          // [KB (head-dim halves)][128 kv rows][128 B]
   static constexpr int P_BYTES = 2 * kAtBQ * 128;            // [2 kv k-blocks][128 rows][128 B]
-  // hd 128: one CTA per SM (192 KB of shared memory), so the CTA overlaps its own phases: 2 K/V stages, 2 score buffers in TMEM.
-  // hd 64: TWO CTAs per SM (80 KB, 256 TMEM columns each) overlap each other instead: 1 K/V stage, 1 score buffer.
-  static constexpr int NSTAGE = HD == 64 ? 1 : 2;
-  static constexpr int NSBUF = HD == 64 ? 1 : 2;
-  static constexpr int CTAS_PER_SM = HD == 64 ? 2 : 1;
+  // TWO CTAs per SM overlap each other's phases (one CTA's softmax runs while the other's MMAs and TMA loads do): 1 K/V stage,
+  // 1 score buffer, 256 TMEM columns each.  (Measured under ncu: one CTA per SM with 2 stages / 2 score buffers left the tensor pipe
+  // 6-12 % active.)  hd 128: P (32 KB) is written over the K tile of the same iteration -- K is dead once S = Q K^T has completed
+  // (the softmax waits for exactly that), and the next K is loaded only after P V has completed (the commit that frees the stage) --
+  // which brings the CTA to 96 KB.  hd 64: K is only 16 KB, P keeps its own buffer (80 KB).
+  static constexpr int NSTAGE = 1;
+  static constexpr int NSBUF = 1;
+  static constexpr int CTAS_PER_SM = 2;
   static constexpr int KV_OFF = Q_BYTES;
-  static constexpr int P_OFF = KV_OFF + NSTAGE * (K_BYTES + V_BYTES);
-  static constexpr int BAR_OFF = P_OFF + P_BYTES;
+  static constexpr bool P_ALIASES_K = (K_BYTES >= P_BYTES);
+  static constexpr int P_OFF = P_ALIASES_K ? KV_OFF : KV_OFF + NSTAGE * (K_BYTES + V_BYTES);
+  static constexpr int BAR_OFF = P_ALIASES_K ? KV_OFF + NSTAGE * (K_BYTES + V_BYTES) : P_OFF + P_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
-  static constexpr int TMEM_COLS = HD == 64 ? 256 : 512;     // S: NSBUF x 128 columns, then O: HD columns
+  static constexpr int TMEM_COLS = 256;                      // S: 128 columns, then O: HD columns
   static constexpr uint32_t O_COL = NSBUF * 128;
 };
 

@@ -156,7 +156,7 @@ struct AttnCall {
 int attention_prefill(const AttnCall& c, cudaStream_t st);      // dispatches to the tcgen05 kernel (attention_tc.cu) unless switched off
 int attention_prefill_tc(const AttnCall& c, cudaStream_t st);   // tcgen05: QK^T and PV as UMMA, S / O in TMEM, Q / K / V by TMA
 int attention_prefill_mma(const AttnCall& c, cudaStream_t st);  // mma.sync m16n8k16 fallback (attention.cu)
-void attention_set_tc(int on);                                   // 1: tcgen05 kernel, 0: mma.sync kernel (VCLA_ATTN_TC)
+void attention_set_tc(int mode);                                 // 0: mma.sync everywhere, 1 (default): tcgen05 at head dim 128, 2: tcgen05 everywhere (VCLA_ATTN_TC)
 int trace_set_attention_tc(void* buf, unsigned long long cap);
 
 struct DecodeAttnCall {
