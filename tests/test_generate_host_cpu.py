@@ -171,3 +171,114 @@ def test_sampling_knobs_and_stopping_criteria():
     # repetition penalty changes the logits path but must keep shapes / dtypes
     rp = m.generate(input_ids=ids, do_sample=False, repetition_penalty=1.3, max_new_tokens=5, eos_token_id=None, pad_token_id=0)
     assert rp.shape == (1, 5)
+
+
+class SamplerEngine(FakeEngine):
+    """FakeEngine + the device-sampler surface: records the spec the host hands to the native side and emulates the in-graph
+    loop (EOS flags, pad after EOS) so that generate()'s device path can be followed on the CPU."""
+
+    def __init__(self):
+        super().__init__()
+        self.spec, self.set_calls, self.fin = None, [], None
+
+    def sampler_supported(self):
+        return True
+
+    @staticmethod
+    def sampler_spec(**kw):
+        return dict(kw)
+
+    def set_sampler(self, spec):
+        self.set_calls.append(spec)
+        self.spec = spec
+
+    def prefill(self, ids, mode, rows, all_logits=False, last_logits=True, left_pad=None, pos_from_mask=True):
+        out = super().prefill(ids, mode, rows, all_logits, last_logits, left_pad, pos_from_mask)
+        self.fin = torch.zeros(ids.shape[0], dtype=torch.bool)
+        self._mark(self.hist[0])
+        return out
+
+    def _mark(self, tok):
+        for e in (self.spec or {}).get("eos_token_id", ()):
+            self.fin |= tok.long() == e
+
+    def decode_step(self, tok_in, tok_out, logits=None, use_graph=True):
+        was = self.fin.clone()
+        super().decode_step(tok_in, tok_out, logits, use_graph)
+        if self.spec is not None:
+            tok_out[was] = self.spec["pad_token_id"]
+            self.hist[-1] = tok_out.clone()
+            self._mark(torch.where(was, torch.full_like(tok_out, -1), tok_out))
+
+    def read_finished(self, B):
+        return self.fin.to(torch.int32)
+
+
+def make_sampler_model():
+    m = make_model()
+    m._engine = SamplerEngine()
+    return m
+
+
+def test_device_sampler_is_chosen_exactly_when_the_config_allows(monkeypatch):
+    """Host-side decision of VisualCLAModel._device_sampler_spec: the reference's DEFAULT_GENERATION_CONFIG and greedy+EOS /
+    greedy+penalties run on the device (one native spec, no per-step host work); everything the fused kernel does not cover keeps
+    the host logits-processor path."""
+    from visualcla.modeling_utils import DEFAULT_GENERATION_CONFIG
+    ids = torch.tensor([[1, 5, 9], [1, 6, 11]])
+    m = make_sampler_model()
+    torch.manual_seed(3)
+    m.generate(input_ids=ids, generation_config=DEFAULT_GENERATION_CONFIG, max_new_tokens=4, eos_token_id=None, pad_token_id=0)
+    spec = m._engine.set_calls[0]
+    assert m._engine.set_calls[-1] is None, "the sampler is switched off again after the call"
+    assert (spec["do_sample"], spec["top_k"], spec["no_repeat_ngram_size"], spec["eos_token_id"]) == (True, 40, 15, [])
+    assert abs(spec["temperature"] - 0.5) < 1e-9 and abs(spec["top_p"] - 0.9) < 1e-9 and abs(spec["repetition_penalty"] - 1.1) < 1e-9
+    torch.manual_seed(3)
+    m2 = make_sampler_model()
+    m2.generate(input_ids=ids, generation_config=DEFAULT_GENERATION_CONFIG, max_new_tokens=4, eos_token_id=None, pad_token_id=0)
+    assert m2._engine.set_calls[0]["seed"] == spec["seed"], "torch.manual_seed reproduces the Philox seed"
+
+    def used_device(**kw):
+        mm = make_sampler_model()
+        mm.generate(input_ids=ids[:1], max_new_tokens=4, pad_token_id=0, **kw)     # one row: the reference's Mirostat only handles batch 1
+        return len(mm._engine.set_calls) > 0
+
+    assert not used_device(do_sample=False, eos_token_id=None)                                   # plain greedy: the argmax graphs
+    assert used_device(do_sample=False, eos_token_id=7)                                          # greedy + EOS: sticky flags on the device
+    assert used_device(do_sample=False, eos_token_id=None, repetition_penalty=1.2)
+    assert used_device(do_sample=True, top_k=5, eos_token_id=None)
+    assert not used_device(do_sample=True, top_k=0, top_p=0.9, eos_token_id=None)               # top-k disabled: host path
+    assert not used_device(do_sample=True, top_k=5, tfs=0.9, eos_token_id=None)
+    assert not used_device(do_sample=True, top_k=5, mirostat_mode=2, eos_token_id=None)
+    assert not used_device(do_sample=True, top_k=5, eos_token_id=None, output_logits=True, return_dict_in_generate=True)
+    assert not used_device(do_sample=True, top_k=5, eos_token_id=None, stopping_criteria=[lambda i, s: False])
+    assert not used_device(do_sample=False, eos_token_id=[1, 2, 3, 4, 5])                       # more EOS ids than the native spec holds
+    monkeypatch.setenv("VCLA_HOST_SAMPLER", "1")
+    assert not used_device(do_sample=True, top_k=5, eos_token_id=None)
+
+
+def test_device_eos_path_matches_host_path():
+    """Greedy + EOS through the device path (graphs of 8 steps, finished flags polled between them) returns exactly what the
+    per-step host path returns: pad after a row's EOS, cut where the last row finished."""
+    ids = torch.tensor([[1, 5, 9], [1, 6, 11]])
+    full = make_model().generate(input_ids=ids, do_sample=False, max_new_tokens=20, eos_token_id=None, pad_token_id=0)
+    for eos in (int(full[0, 2]), int(full[1, 10]), [int(full[0, 1]), int(full[1, 4])]):
+        host = make_model().generate(input_ids=ids, do_sample=False, max_new_tokens=20, eos_token_id=eos, pad_token_id=49)
+        dev_m = make_sampler_model()
+        dev = dev_m.generate(input_ids=ids, do_sample=False, max_new_tokens=20, eos_token_id=eos, pad_token_id=49)
+        assert dev_m._engine.set_calls and dev.shape == host.shape and torch.equal(dev, host), (eos, dev.tolist(), host.tolist())
+
+
+def test_mirostat_wiring_replays_the_reference_quirk():
+    """ref modeling_utils.py:366-371 removes the non-temperature warpers while iterating over them, which skips every second one:
+    with temperature, top-k and top-p configured, top-p survives next to Mirostat."""
+    from transformers import GenerationConfig
+    from transformers.generation import logits_process as lp
+    from visualcla import modeling_utils as mu
+    gc = GenerationConfig(do_sample=True, temperature=0.7, top_k=40, top_p=0.9, repetition_penalty=1.1)
+    gc.mirostat_mode, gc.mirostat_tau, gc.mirostat_eta = 2, 5.0, 0.1
+    procs = VisualCLAModel._build_processors(gc, None)
+    kinds = [type(p) for p in procs]
+    assert kinds == [lp.RepetitionPenaltyLogitsProcessor, lp.TemperatureLogitsWarper, lp.TopPLogitsWarper, mu.MirostatLogitsWarper]
+    gc.mirostat_mode = 0
+    assert mu.MirostatLogitsWarper not in [type(p) for p in VisualCLAModel._build_processors(gc, None)]
