@@ -1,5 +1,7 @@
-// tcgen05 flash attention for the prefill side of the path (sm_100a): ViT self-attention (257 tokens, hd 64), the Resampler's
-// 64 queries over [their own 64 rows ; 257 image rows] (two KV segments, hd 64) and LLaMA's causal prefill (hd 128).
+// tcgen05 flash attention for the prefill side of the path (sm_100a): LLaMA's causal prefill (hd 128) by default; it also covers
+// ViT self-attention (257 tokens, hd 64) and the Resampler's 64 queries over [their own 64 rows ; 257 image rows] (two KV segments,
+// hd 64), which the default dispatch leaves on the mma.sync kernel because the 128-row tile wastes a third of its work there
+// (attention.cu: attention_prefill; VCLA_ATTN_TC=2 forces this kernel everywhere, and the tests run it on every shape).
 //
 // One CTA per (128 query rows, head, sequence).  Both contractions run on the 5th-generation tensor cores:
 //   S = Q K^T   UMMA 128 x 128 x HD   A = Q tile, B = K tile, both K-major [rows][64-element k-blocks] staged by TMA (128 B swizzle);
@@ -12,7 +14,7 @@
 //
 // Warps: 0 = TMA producer (Q once, then the K/V tiles), 1 = MMA issuer + TMEM owner, 2..5 = softmax / rescale /
 // epilogue (thread t owns query row t = TMEM lane t).  Masks: keys past a segment's end, causal (key <= query + Sk - Sq), left padding
-// (kv_start).  Fully masked rows produce zeros, like the mma.sync kernel this replaces (csrc/attention.cu, kept as the fallback).
+// (kv_start).  Fully masked rows produce zeros, like the mma.sync kernel (csrc/attention.cu).
 #include "common.cuh"
 #include "kernels.h"
 

@@ -16,6 +16,10 @@
 // commutes with the GEMM and is applied by the consumer of the NEXT GEMM (a row scalar; bf16's relative rounding is scale free).
 // A decode layer is then 5 kernels (QKV, attention, O, gate/up, down) instead of 8.
 //
+// Reduce buffering (template NBUF): 2 = double buffered (tile t+1's partials may arrive while tile t is being summed; the hand-shake
+// is one remote arrive per peer and tile), 1 = one buffer + a second 'consumed' barrier, which frees shared memory for a deeper TMA
+// ring (used for the 32-column batch tile).  Two CTAs per SM; the launch assumes that occupancy (see csk_max_clusters).
+//
 // Per CTA (192 threads): warp 0 = TMA producer (weight tiles are requested BEFORE griddepcontrol.wait: they never depend on the
 // previous kernel), warp 1 = tcgen05.mma issuer + TMEM owner, warps 2..5 = epilogue: TMEM -> peers' smem -> reduce -> consumer.
 #include "common.cuh"
