@@ -213,7 +213,8 @@ GEMM_BYTES = {"qkv": 3 * 4096 * 4096 * 2, "o_proj": 4096 * 4096 * 2, "gate_up": 
 def insitu_decode_kernels(eng, tok, n_layers=32):
     """Per-kernel time INSIDE a graph-replayed decode step, from the in-kernel %globaltimer trace (vcla_trace_*): a kernel's in-situ
     duration = the time between its own dependency resolving and its successor's dependency resolving (= its whole grid, the
-    launch gap included), so the durations of one step add up to the step.  -> {kernel: mean microseconds}."""
+    launch gap included), so the durations of one step add up to the step.
+    -> ({kernel: mean microseconds}, {kernel: launches counted}, traced span of the step in microseconds)."""
     import torch
     for _ in range(3):
         eng.decode_step(tok, tok, None)          # single-step graph: captured + warm

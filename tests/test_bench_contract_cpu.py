@@ -47,3 +47,42 @@ def test_native_arm_refuses_to_run_without_gpu():
         pytest.skip("has a GPU")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_insitu_trace_labelling_and_durations(bench, monkeypatch):
+    """bench.py's in-situ roofline: kernels of one graph-replayed decode step are labelled by order (per layer qkv, o, gate/up, down; the
+    129th swap-AB GEMM is lm_head) and a kernel's duration is its successor's dependency-resolved time minus its own, so the
+    durations add up to the step."""
+    import torch
+
+    class FakeEngine:
+        def __init__(self):
+            self.enabled = False
+
+        def decode_step(self, *a, **k):
+            pass
+
+        def trace_enable(self, n):
+            self.enabled = n > 0
+
+        def trace_read(self):
+            # (tag, t_entry, t_dep, t_exit) in ns; cluster split-K schedule: embed, 32 x [qkv, attn, o, gate_up, down], lm_head, logits1, logits2, advance
+            t, ev = 1000, [(13, 900, 1000, 0)]
+            per = {"qkv": 17500, "attn": 11000, "o": 10500, "gu": 29500, "d": 19000}
+            for _ in range(32):
+                for tag, key in ((1, "qkv"), (4, "attn"), (1, "o"), (1, "gu"), (1, "d")):
+                    t += {13: 2500}.get(ev[-1][0], 0) if len(ev) == 1 else 0
+                    ev.append((tag, t - 5000, t, t + 100))
+                    t += per[key]
+            for tag, dur in ((1, 61000), (10, 4600), (11, 1600), (12, 2000)):
+                ev.append((tag, t - 1000, t, 0))
+                t += dur
+            return ev
+
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    mean, count, total = bench.insitu_decode_kernels(FakeEngine(), None)
+    assert count["qkv"] == 32 and count["o_proj"] == 32 and count["gate_up"] == 32 and count["down_proj"] == 32 and count["lm_head"] == 1
+    assert mean["gate_up"] == pytest.approx(29.5) and mean["qkv"] == pytest.approx(17.5) and mean["down_proj"] == pytest.approx(19.0)
+    assert mean["lm_head"] == pytest.approx(61.0) and mean["attn_decode"] == pytest.approx(11.0)
+    assert total == pytest.approx(sum(mean[k] * count[k] for k in mean), rel=1e-6)
+    assert bench.GEMM_BYTES["gate_up"] == 2 * 11008 * 4096 * 2 and bench.GEMM_BYTES["lm_head"] == 49958 * 4096 * 2
